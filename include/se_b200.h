@@ -1,0 +1,137 @@
+/* se_b200.h -- C ABI of the B200-native supereight hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, plain pointers
+ * and sizes, row-major 4x4 float poses, no Eigen/torch types.  The C++ class
+ * `DenseSLAMSystem` in supereight_b200/host/ (same public methods as the reference's
+ * se_denseslam/include/se/DenseSLAMSystem.h:58-411) is a thin shim over these calls; a
+ * maintainer of the reference binds the same calls from DenseSLAMSystem.cpp.
+ *
+ * Every entry point names the reference code it replaces (paths relative to the reference
+ * tree).  All functions return 0 on success and a negative code on failure;
+ * se_b200_last_error() gives the message for the calling thread.  There is no CPU fallback:
+ * without a CUDA device every call fails with SE_B200_ERR_CUDA.
+ *
+ * Threading: like the reference (one caller thread drives the stages in order), a map must
+ * not be used from two threads at once.  All work of a map is enqueued on one CUDA stream
+ * (se_b200_set_stream); calls that return data to host memory synchronise that stream, the
+ * others return as soon as the work is enqueued.
+ */
+#ifndef SE_B200_H
+#define SE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct se_b200_map se_b200_map;
+
+/* SE_FIELD_TYPE of the reference (DenseSLAMSystem.h:54, volume_traits.hpp:41-72) */
+enum { SE_B200_SDF = 0, SE_B200_OFUSION = 1 };
+
+enum {
+  SE_B200_OK = 0,
+  SE_B200_ERR_ARG = -1,       /* bad argument (the reference prints "Invalid ratio." and exit(1)s, preprocessing.cpp:165-176) */
+  SE_B200_ERR_CUDA = -2,      /* CUDA runtime error, or no device */
+  SE_B200_ERR_POOL = -3       /* node/block pool exhausted (reference: allocation list silently truncated, kfusion/alloc_impl.hpp:103-106) */
+};
+
+/* voxel payload layouts, identical to the reference structs (volume_traits.hpp:41-44, 62-65) */
+typedef struct { float x; float y; } se_b200_sdf_voxel;                 /* tsdf in [-1,1], weight */
+typedef struct { float x; float pad_; double y; } se_b200_ofusion_voxel; /* log-odds occupancy, timestamp [s] */
+
+const char* se_b200_last_error(void);
+int se_b200_device_count(void);
+
+/* ---- lifetime --------------------------------------------------------------------------
+ * Replaces se::Octree<FieldType>::init (se_core/include/se/octree.hpp:411-421) and the image
+ * members of DenseSLAMSystem (DenseSLAMSystem.cpp:65-126).  The octree lives in device memory
+ * as flat index-addressed pools of `max_nodes` nodes and `max_blocks` 8x8x8 VoxelBlocks
+ * (0 = pick a default from the volume size).  `size` must be a power of two >= 16, `W`x`H` is
+ * the computation size. */
+int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W, int H,
+                   int64_t max_blocks, int64_t max_nodes, int device);
+int se_b200_destroy(se_b200_map* map);
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*; NULL = the map's own stream). */
+int se_b200_set_stream(se_b200_map* map, void* cuda_stream);
+int se_b200_sync(se_b200_map* map);
+
+/* ---- a1: mm2metersKernel (se_denseslam/src/preprocessing.cpp:161-188) -------------------
+ * depth_mm is inW x inH uint16 millimetres; the result is the W x H float depth (metres) that
+ * integration and renderDepth read.  inW/W == inH/H must be a whole ratio.
+ * _host: pointer to host memory (copied inside the call, asynchronously if it is pinned);
+ * _device: pointer to device memory already holding the frame. */
+int se_b200_preprocess_depth_host(se_b200_map* map, const uint16_t* depth_mm, int inW, int inH);
+int se_b200_preprocess_depth_device(se_b200_map* map, const uint16_t* depth_mm_dev, int inW, int inH);
+/* test/IO helper: set the float depth image directly (W*H floats, host memory) */
+int se_b200_set_depth_m_host(se_b200_map* map, const float* depth_m);
+
+/* ---- a3..a12: the body of DenseSLAMSystem::integration (DenseSLAMSystem.cpp:211-253) ----
+ * buildAllocationList / buildOctantList (kfusion|bfusion/alloc_impl.hpp) + Octree::allocate
+ * (octree.hpp:792-856) + se::functor::projective_map (functors/projective_functor.hpp:139-156)
+ * with sdf_update / bfusion_update.  pose = camera-to-world, k = (fx, fy, cx, cy), `frame`
+ * only feeds the OFusion timestamp frame/30.  The frame gate (frame % rate) stays in the caller. */
+int se_b200_integrate(se_b200_map* map, const float pose[16], const float k[4], float mu, unsigned frame);
+
+/* ---- a13..a17: raycastKernel (se_denseslam/src/rendering.cpp:50-90) ---------------------
+ * view = pose * K^-1, near/far planes 0.4/4.0 m (constant_parameters.h:27,32), step = one
+ * voxel, largestep = one block (DenseSLAMSystem.cpp:197-200).  Vertex and normal maps stay on
+ * the device (W*H*3 floats each, row-major, as se::Image<Eigen::Vector3f>). */
+int se_b200_raycast(se_b200_map* map, const float pose[16], const float k[4], float mu);
+int se_b200_download_vertex_normal(se_b200_map* map, float* vertex, float* normal);   /* either may be NULL */
+int se_b200_upload_vertex_normal(se_b200_map* map, const float* vertex, const float* normal);
+
+/* ---- a18: renderVolumeKernel / renderDepthKernel / renderTrackKernel --------------------
+ * (rendering.cpp:214-283, 111-152, 154-212).  out is W*H*4 bytes RGBA, caller-owned, as in
+ * the reference (benchmark.cpp:90-97).  reraycast != 0 is the reference's `render` flag (view
+ * pose differs from the raycast pose: cast again from the volume entry with far plane 8 m);
+ * 0 shades the stored vertex/normal maps.  light = translation of view_pose.
+ * track_result: W*H ints `stride_ints` apart (TrackData::result, commons.h:228-232 -> stride 8). */
+int se_b200_render_volume_host(se_b200_map* map, uint8_t* out, const float view_pose[16], const float k[4],
+                               float mu, float largestep, int reraycast);
+int se_b200_render_volume_device(se_b200_map* map, uint8_t* out_dev, const float view_pose[16], const float k[4],
+                                 float mu, float largestep, int reraycast);
+int se_b200_render_depth_host(se_b200_map* map, uint8_t* out);
+int se_b200_render_track_host(se_b200_map* map, uint8_t* out, const int* track_result, int stride_ints);
+
+/* ---- inspection: what getMap() / Octree::save expose in the reference --------------------
+ * (DenseSLAMSystem.h:295-297, octree.hpp:897-915).  Pool order is arbitrary in the reference
+ * (OpenMP scheduling) and here (atomics); "sorted" = ascending key, the comparable form.
+ * Any output pointer may be NULL.  voxels: n*512 payload structs; values: n*8. */
+int se_b200_block_count(se_b200_map* map, int* out);
+int se_b200_node_count(se_b200_map* map, int* out);
+int se_b200_download_blocks_sorted(se_b200_map* map, uint64_t* keys, int32_t* coords_xyz, uint8_t* active, void* voxels);
+int se_b200_download_nodes_sorted(se_b200_map* map, uint64_t* codes, uint32_t* side, uint8_t* children_mask, void* values);
+/* Octree::allocate for an explicit key list (octree.hpp:792-817), incl. multi-level keys */
+int se_b200_allocate_keys(se_b200_map* map, const uint64_t* keys, int n);
+/* point queries, n points each: get_fine (octree.hpp:356-377) at integer voxels, interp
+ * (:541-563) and grad (:652-737) at float voxel positions, Octree::set (:310-329) */
+int se_b200_query_voxels(se_b200_map* map, const int32_t* xyz, int n, void* voxels_out);
+int se_b200_query_interp(se_b200_map* map, const float* pos_xyz, int n, float* out);
+int se_b200_query_grad(se_b200_map* map, const float* pos_xyz, int n, float* out_xyz);
+int se_b200_set_voxels(se_b200_map* map, const int32_t* xyz, const void* voxels, int n);
+/* se::ray_iterator (ray_iterator.hpp:49-289): first block on each ray (key, or ~0) and
+ * (tmin, tmax, tcmin) in metres.  origin_dir: n * (ox,oy,oz,dx,dy,dz). */
+int se_b200_query_rays(se_b200_map* map, const float* origin_dir, int n, float near_plane, float far_plane,
+                       uint64_t* first_block_key, float* tmin_tmax_tcmin);
+
+/* ---- measurement ------------------------------------------------------------------------
+ * Device time of the most recent run of a stage (CUDA events on the map's stream); stands in
+ * for the TICK/TOCK samples of se_shared/timings.h:7-15. */
+enum { SE_B200_STAGE_PREPROCESS = 0, SE_B200_STAGE_ALLOC = 1, SE_B200_STAGE_FUSE = 2, SE_B200_STAGE_RAYCAST = 3,
+       SE_B200_STAGE_RENDER = 4, SE_B200_NUM_STAGES = 5 };
+int se_b200_elapsed_ms(se_b200_map* map, int stage, float* ms);
+/* counters of the last integrate: [0] nodes, [1] blocks, [2] active blocks, [3] error bits,
+ * [4] blocks before the frame, [5] nodes before the frame, [6] octant requests (OFusion) */
+int se_b200_counters(se_b200_map* map, int32_t out[8]);
+/* number of kernels this library has launched on behalf of `map` so far */
+int se_b200_launch_count(se_b200_map* map, int64_t* out);
+/* device pointers of the map's images, for callers that keep data resident:
+ * 0 float depth [W*H], 1 vertex [W*H*3], 2 normal [W*H*3] */
+int se_b200_device_image(se_b200_map* map, int which, void** ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE_B200_H */

@@ -1,0 +1,736 @@
+// se_b200.cu -- implementation of the C ABI in include/se_b200.h (one translation unit, like
+// the reference's unity build of DenseSLAMSystem.cpp:44-50).
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -Xcompiler -fPIC,-ffp-contract=off -shared -o libse_b200.so se_b200.cu
+// -fmad=false / -ffp-contract=off are part of the arithmetic contract (se_math.cuh).
+#include "../../include/se_b200.h"
+#include "se_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace se_b200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) { g_error = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      return fail(SE_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+    }                                                                                           \
+  } while (0)
+
+struct Pools {
+  int* node_child = nullptr;
+  unsigned long long* node_code = nullptr;
+  unsigned int* node_side = nullptr;
+  unsigned int* node_mask = nullptr;
+  void* node_value = nullptr;
+  unsigned long long* block_code = nullptr;
+  int4* block_coord = nullptr;
+  int* block_active = nullptr;
+  void* block_data = nullptr;
+  int* counters = nullptr;
+};
+
+}  // namespace
+
+struct se_b200_map {
+  int field = 0, size = 0, W = 0, H = 0, device = 0;
+  float dim = 0.f;
+  int max_level = 0, leaves_level = 0;
+  int max_nodes = 0, max_blocks = 0, max_requests = 0;
+  int num_sms = 148;
+  size_t voxel_bytes = 8;
+  Pools p;
+  float* d_depth = nullptr;
+  float* d_vertex = nullptr;
+  float* d_normal = nullptr;
+  uchar4* d_rgba = nullptr;
+  unsigned short* d_depth_mm = nullptr;
+  size_t depth_mm_capacity = 0;
+  int* d_active_list = nullptr;
+  unsigned long long* d_requests = nullptr;
+  int* d_track = nullptr;
+  size_t track_capacity = 0;
+  int* h_counters = nullptr;              // pinned
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev_begin[SE_B200_NUM_STAGES] = {}, ev_end[SE_B200_NUM_STAGES] = {};
+  bool ev_valid[SE_B200_NUM_STAGES] = {};
+  long long launches = 0;
+
+  template <class V> MapView<V> view() const {
+    MapView<V> v;
+    v.size = size; v.dim = dim; v.max_level = max_level; v.leaves_level = leaves_level;
+    v.max_nodes = max_nodes; v.max_blocks = max_blocks;
+    v.node_child = p.node_child; v.node_code = p.node_code; v.node_side = p.node_side; v.node_mask = p.node_mask;
+    v.node_value = (V*)p.node_value;
+    v.block_code = p.block_code; v.block_coord = p.block_coord; v.block_active = p.block_active;
+    v.block_data = (V*)p.block_data;
+    v.counters = p.counters;
+    return v;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+M4 to_m4(const float* p) { M4 m; std::memcpy(m.m, p, sizeof(m.m)); return m; }
+
+int check_launch(se_b200_map* m, int n = 1) {
+  m->launches += n;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SE_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return SE_B200_OK;
+}
+
+void stage_begin(se_b200_map* m, int s) { cudaEventRecord(m->ev_begin[s], m->stream); }
+void stage_end(se_b200_map* m, int s) { cudaEventRecord(m->ev_end[s], m->stream); m->ev_valid[s] = true; }
+
+// B-spline table of bfusion/bspline_lookup.cc:36-37, regenerated from the closed form it samples
+// (mapping_impl.hpp:94-106) at t = -3 + 6 i / 999; tests pin it against a checksum of the original.
+float bspline_closed(float t) {
+  float value = 0.f;
+  if (t >= -3.0f && t <= -1.0f) value = (float)(std::pow((double)(3 + t), 3) / 48.0f);
+  else if (t > -1 && t <= 1) value = 0.5f + (t * (3 + t) * (3 - t)) / 24.f;
+  else if (t > 1 && t <= 3) value = (float)(1 - std::pow((double)(3 - t), 3) / 48.f);
+  else if (t > 3) value = 1.f;
+  return value;
+}
+
+int pixel_tile_blocks(int W, int H, int threads) {
+  const int tiles = ((W + 7) / 8) * ((H + 3) / 4);
+  const int warps_per_block = threads / 32;
+  return (tiles + warps_per_block - 1) / warps_per_block;
+}
+
+template <class V>
+int create_pools(se_b200_map* m) {
+  const size_t nn = (size_t)m->max_nodes, nb = (size_t)m->max_blocks;
+  CUDA_TRY(cudaMalloc(&m->p.node_child, nn * 8 * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&m->p.node_code, nn * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&m->p.node_side, nn * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&m->p.node_mask, nn * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&m->p.node_value, nn * 8 * sizeof(V)));
+  CUDA_TRY(cudaMalloc(&m->p.block_code, nb * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&m->p.block_coord, nb * sizeof(int4)));
+  CUDA_TRY(cudaMalloc(&m->p.block_active, nb * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&m->p.block_data, nb * kBlockVoxels * sizeof(V)));
+  CUDA_TRY(cudaMalloc(&m->p.counters, kNumCounters * sizeof(int)));
+  CUDA_TRY(cudaMemsetAsync(m->p.node_child, 0xFF, nn * 8 * sizeof(int), m->stream));      // kEmpty
+  CUDA_TRY(cudaMemsetAsync(m->p.node_code, 0, nn * sizeof(unsigned long long), m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.node_side, 0, nn * sizeof(unsigned), m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.node_mask, 0, nn * sizeof(unsigned), m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.block_code, 0, nb * sizeof(unsigned long long), m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.block_coord, 0, nb * sizeof(int4), m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.block_active, 0, nb * sizeof(int), m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.counters, 0, kNumCounters * sizeof(int), m->stream));
+  const int grid = m->num_sms * 8;
+  k_fill_voxels<V><<<grid, 256, 0, m->stream>>>((V*)m->p.node_value, nn * 8);
+  k_fill_voxels<V><<<grid, 256, 0, m->stream>>>((V*)m->p.block_data, nb * kBlockVoxels);
+  if (int r = check_launch(m, 2)) return r;
+  // root: Octree::init (octree.hpp:411-421): node 0, code 0, side = size
+  const int one = 1;
+  const unsigned side = (unsigned)m->size;
+  CUDA_TRY(cudaMemcpyAsync(m->p.counters + kCntNodes, &one, sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(m->p.node_side, &side, sizeof(unsigned), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int fetch_counters(se_b200_map* m) {
+  CUDA_TRY(cudaMemcpyAsync(m->h_counters, m->p.counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+template <class V>
+int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu, unsigned frame) {
+  const M4 pose = to_m4(pose_p);
+  const float voxelsize = m->dim / (float)m->size;                       // DenseSLAMSystem.cpp:211
+  const float band = FieldTraits<V>::is_sdf ? 2 * mu : 6 * mu;           // :223, :228
+  MapView<V> view = m->view<V>();
+
+  AllocParams ap;
+  ap.kPose = mul44(pose, inverse_camera_matrix(k));
+  ap.camera = v3(pose.m[3], pose.m[7], pose.m[11]);
+  ap.inverseVoxelSize = 1 / voxelsize;
+  ap.voxelSize = voxelsize;
+  ap.band = band;
+  ap.numSteps = (int)std::ceil(band * ap.inverseVoxelSize);
+  ap.W = m->W; ap.H = m->H;
+
+  // counters: remember the pool sizes before the frame, clear the per-frame ones
+  stage_begin(m, SE_B200_STAGE_ALLOC);
+  CUDA_TRY(cudaMemcpyAsync(m->p.counters + kCntNewBlocksBase, m->p.counters + kCntBlocks, sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(m->p.counters + kCntNewNodesBase, m->p.counters + kCntNodes, sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.counters + kCntActive, 0, sizeof(int), m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->p.counters + kCntKeys, 0, sizeof(int), m->stream));
+  const int threads = 256;
+  const int grid_px = pixel_tile_blocks(m->W, m->H, threads);
+  if (FieldTraits<V>::is_sdf) {
+    k_alloc_sdf<V><<<grid_px, threads, 0, m->stream>>>(view, m->d_depth, ap);
+    if (int r = check_launch(m)) return r;
+  } else {
+    k_alloc_ofusion<V><<<grid_px, threads, 0, m->stream>>>(view, m->d_depth, ap, m->d_requests, m->max_requests);
+    k_alloc_first_key_chain<V><<<1, 1024, 0, m->stream>>>(view, m->d_requests, m->max_requests);
+    if (int r = check_launch(m, 2)) return r;
+  }
+  stage_end(m, SE_B200_STAGE_ALLOC);
+
+  stage_begin(m, SE_B200_STAGE_FUSE);
+  const M4 Tcw = rigid_inverse(pose);
+  const M4 K = camera_matrix(k);
+  FrustumParams fp;
+  fp.cam = mul44(K, Tcw);
+  fp.voxelSize = voxelsize; fp.W = m->W; fp.H = m->H;
+  IntegrateParams ip;
+  ip.Tcw = Tcw; ip.K = K;
+  ip.delta = rot3(Tcw, v3(voxelsize, 0.f, 0.f));
+  ip.cameraDelta = rot3(K, ip.delta);
+  ip.voxelSize = voxelsize; ip.mu = mu;
+  ip.timestamp = (1.f / 30.f) * (float)frame;                            // DenseSLAMSystem.cpp:243
+  ip.W = m->W; ip.H = m->H;
+  const int grid = m->num_sms * 8;          // 8 CTAs x 8 warps per SM: persistent grid-stride loops
+  k_active_list<V><<<grid, threads, 0, m->stream>>>(view, fp, m->d_active_list);
+  if (FieldTraits<V>::is_sdf)
+    k_integrate_sdf<<<grid, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
+  else
+    k_integrate_ofusion<<<grid, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list);
+  k_update_nodes<V><<<std::max(1, m->num_sms), threads, 0, m->stream>>>(view, m->d_depth, ip);
+  if (int r = check_launch(m, 3)) return r;
+  stage_end(m, SE_B200_STAGE_FUSE);
+  return SE_B200_OK;
+}
+
+RaycastParams make_raycast_params(se_b200_map* m, const float* pose, const float* k, float mu, float farPlane, float largestep, int use_tcmin) {
+  RaycastParams rp;
+  rp.view = mul44(to_m4(pose), inverse_camera_matrix(k));
+  rp.nearPlane = kNearPlane; rp.farPlane = farPlane; rp.mu = mu;
+  rp.step = m->dim / (float)m->size;                                      // DenseSLAMSystem.cpp:197, :282
+  rp.largestep = largestep;
+  rp.W = m->W; rp.H = m->H; rp.use_tcmin = use_tcmin;
+  return rp;
+}
+
+template <class V>
+int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu) {
+  const float step = m->dim / (float)m->size;
+  const RaycastParams rp = make_raycast_params(m, pose, k, mu, kFarPlane, step * (float)kBlockSide, 1);
+  stage_begin(m, SE_B200_STAGE_RAYCAST);
+  k_raycast<V><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal);
+  if (int r = check_launch(m)) return r;
+  stage_end(m, SE_B200_STAGE_RAYCAST);
+  return SE_B200_OK;
+}
+
+template <class V>
+int render_volume_impl(se_b200_map* m, uchar4* out_dev, const float* view_pose, const float* k, float mu, float largestep, int reraycast) {
+  const RaycastParams rp = make_raycast_params(m, view_pose, k, mu, kFarPlane * 2.0f, largestep, 0);   // DenseSLAMSystem.cpp:283-288
+  const V3 light = v3(view_pose[3], view_pose[7], view_pose[11]);
+  stage_begin(m, SE_B200_STAGE_RENDER);
+  k_render_volume<V><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, light, reraycast, m->d_vertex, m->d_normal, out_dev);
+  if (int r = check_launch(m)) return r;
+  stage_end(m, SE_B200_STAGE_RENDER);
+  return SE_B200_OK;
+}
+
+template <class V>
+int download_blocks_sorted_impl(se_b200_map* m, uint64_t* keys, int32_t* coords, uint8_t* active, void* voxels) {
+  if (int r = fetch_counters(m)) return r;
+  const int n = std::min(m->h_counters[kCntBlocks], m->max_blocks);
+  std::vector<unsigned long long> code(n);
+  std::vector<int4> coord(n);
+  std::vector<int> act(n);
+  CUDA_TRY(cudaMemcpyAsync(code.data(), m->p.block_code, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(coord.data(), m->p.block_coord, (size_t)n * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(act.data(), m->p.block_active, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
+  std::vector<V> tmp;
+  if (voxels) {
+    tmp.resize((size_t)n * kBlockVoxels);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), m->p.block_data, (size_t)n * kBlockVoxels * sizeof(V), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    const int s = order[i];
+    if (keys) keys[i] = code[s];
+    if (coords) { coords[3 * i] = coord[s].x; coords[3 * i + 1] = coord[s].y; coords[3 * i + 2] = coord[s].z; }
+    if (active) active[i] = act[s] ? 1 : 0;
+    if (voxels) std::memcpy((V*)voxels + (size_t)i * kBlockVoxels, tmp.data() + (size_t)s * kBlockVoxels, sizeof(V) * kBlockVoxels);
+  }
+  return SE_B200_OK;
+}
+
+template <class V>
+int download_nodes_sorted_impl(se_b200_map* m, uint64_t* codes, uint32_t* side, uint8_t* mask, void* values) {
+  if (int r = fetch_counters(m)) return r;
+  const int n = std::min(m->h_counters[kCntNodes], m->max_nodes);
+  std::vector<unsigned long long> code(n);
+  std::vector<unsigned> sd(n), mk(n);
+  std::vector<V> val((size_t)n * 8);
+  CUDA_TRY(cudaMemcpyAsync(code.data(), m->p.node_code, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(sd.data(), m->p.node_side, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(mk.data(), m->p.node_mask, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(val.data(), m->p.node_value, (size_t)n * 8 * sizeof(V), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
+  for (int i = 0; i < n; ++i) {
+    const int s = order[i];
+    if (codes) codes[i] = code[s];
+    if (side) side[i] = sd[s];
+    if (mask) mask[i] = (uint8_t)mk[s];
+    if (values) std::memcpy((V*)values + (size_t)i * 8, val.data() + (size_t)s * 8, sizeof(V) * 8);
+  }
+  return SE_B200_OK;
+}
+
+// scratch device buffer helper for the query entry points (not on the hot path)
+struct Scratch {
+  void* p = nullptr;
+  ~Scratch() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+};
+
+int check_pool_error(se_b200_map* m) {
+  const int err = m->h_counters[kCntError];
+  if (err & kErrBlockPoolFull) return fail(SE_B200_ERR_POOL, "VoxelBlock pool exhausted: raise max_blocks");
+  if (err & kErrNodePoolFull) return fail(SE_B200_ERR_POOL, "node pool exhausted: raise max_nodes");
+  if (err & kErrKeyListFull) return fail(SE_B200_ERR_POOL, "octant request list exhausted");
+  return SE_B200_OK;
+}
+
+}  // namespace
+
+#define FIELD_DISPATCH(m, call_sdf, call_ofu) ((m)->field == SE_B200_SDF ? (call_sdf) : (call_ofu))
+#define REQUIRE_MAP(m) do { if (!(m)) return fail(SE_B200_ERR_ARG, "null map"); } while (0)
+
+extern "C" {
+
+const char* se_b200_last_error(void) { return g_error.c_str(); }
+
+int se_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W, int H,
+                   int64_t max_blocks, int64_t max_nodes, int device) {
+  if (!out) return fail(SE_B200_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (field_type != SE_B200_SDF && field_type != SE_B200_OFUSION) return fail(SE_B200_ERR_ARG, "field_type must be SE_B200_SDF or SE_B200_OFUSION");
+  if (size < 16 || (size & (size - 1)) != 0 || size > (1 << 15)) return fail(SE_B200_ERR_ARG, "size must be a power of two in [16, 32768]");
+  if (!(dim > 0.f) || W <= 0 || H <= 0) return fail(SE_B200_ERR_ARG, "dim, W, H must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SE_B200_ERR_CUDA, "no CUDA device: this library has no CPU fallback"); }
+  if (device < 0 || device >= ndev) return fail(SE_B200_ERR_ARG, "bad device index");
+  DeviceGuard guard(device);
+
+  se_b200_map* m = new se_b200_map;
+  m->field = field_type; m->size = size; m->dim = dim; m->W = W; m->H = H; m->device = device;
+  m->max_level = 0; while ((1 << m->max_level) < size) ++m->max_level;
+  m->leaves_level = m->max_level - 3;
+  m->voxel_bytes = field_type == SE_B200_SDF ? sizeof(SdfVoxel) : sizeof(OfuVoxel);
+  const int64_t grid_blocks = (int64_t)(size / 8) * (size / 8) * (size / 8);
+  if (max_blocks <= 0) max_blocks = std::min<int64_t>(grid_blocks, 1 << 18);
+  max_blocks = std::min<int64_t>(max_blocks, grid_blocks);
+  if (max_nodes <= 0) max_nodes = max_blocks / 4 + 4096;
+  if (max_blocks > (1ll << 30) || max_nodes > (1ll << 28)) { delete m; return fail(SE_B200_ERR_ARG, "pool sizes too large"); }
+  m->max_blocks = (int)max_blocks; m->max_nodes = (int)max_nodes;
+  m->max_requests = m->max_blocks + m->max_nodes;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->num_sms = prop.multiProcessorCount;
+
+  auto cleanup = [&](int code) { se_b200_destroy(m); return code; };
+#define CREATE_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(SE_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); return cleanup(SE_B200_ERR_CUDA); } } while (0)
+  CREATE_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  m->stream = m->own_stream;
+  for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { CREATE_TRY(cudaEventCreate(&m->ev_begin[i])); CREATE_TRY(cudaEventCreate(&m->ev_end[i])); }
+  CREATE_TRY(cudaMallocHost(&m->h_counters, kNumCounters * sizeof(int)));
+  const size_t npx = (size_t)W * H;
+  CREATE_TRY(cudaMalloc(&m->d_depth, npx * sizeof(float)));
+  CREATE_TRY(cudaMalloc(&m->d_vertex, npx * 3 * sizeof(float)));
+  CREATE_TRY(cudaMalloc(&m->d_normal, npx * 3 * sizeof(float)));
+  CREATE_TRY(cudaMalloc(&m->d_rgba, npx * sizeof(uchar4)));
+  CREATE_TRY(cudaMalloc(&m->d_active_list, (size_t)m->max_blocks * sizeof(int)));
+  CREATE_TRY(cudaMemsetAsync(m->d_depth, 0, npx * sizeof(float), m->stream));
+  CREATE_TRY(cudaMemsetAsync(m->d_vertex, 0, npx * 3 * sizeof(float), m->stream));
+  CREATE_TRY(cudaMemsetAsync(m->d_normal, 0, npx * 3 * sizeof(float), m->stream));
+  if (field_type == SE_B200_OFUSION) {
+    CREATE_TRY(cudaMalloc(&m->d_requests, (size_t)m->max_requests * sizeof(unsigned long long)));
+    float lut[1000];
+    for (int i = 0; i < 1000; ++i) lut[i] = bspline_closed(-3.f + 6.f * (float)i / 999.f);
+    CREATE_TRY(cudaMemcpyToSymbol(c_bspline_lut, lut, sizeof(lut)));
+  }
+#undef CREATE_TRY
+  const int r = field_type == SE_B200_SDF ? create_pools<SdfVoxel>(m) : create_pools<OfuVoxel>(m);
+  if (r) return cleanup(r);
+  *out = m;
+  return SE_B200_OK;
+}
+
+int se_b200_destroy(se_b200_map* m) {
+  if (!m) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  cudaFree(m->p.node_child); cudaFree(m->p.node_code); cudaFree(m->p.node_side); cudaFree(m->p.node_mask); cudaFree(m->p.node_value);
+  cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters);
+  cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
+  cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_track);
+  if (m->h_counters) cudaFreeHost(m->h_counters);
+  for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { if (m->ev_begin[i]) cudaEventDestroy(m->ev_begin[i]); if (m->ev_end[i]) cudaEventDestroy(m->ev_end[i]); }
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  cudaGetLastError();
+  delete m;
+  return SE_B200_OK;
+}
+
+int se_b200_set_stream(se_b200_map* m, void* s) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  m->stream = s ? (cudaStream_t)s : m->own_stream;
+  for (bool& v : m->ev_valid) v = false;
+  return SE_B200_OK;
+}
+
+int se_b200_sync(se_b200_map* m) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+static int preprocess_common(se_b200_map* m, const uint16_t* src_dev, int inW, int inH) {
+  const int ratio = inW / m->W;
+  dim3 block(32, 8), grid((m->W + 31) / 32, (m->H + 7) / 8);
+  k_mm2meters<<<grid, block, 0, m->stream>>>(m->d_depth, src_dev, m->W, m->H, inW, ratio);
+  return check_launch(m);
+}
+static int check_ratio(se_b200_map* m, int inW, int inH) {
+  // preprocessing.cpp:165-176 ("Invalid ratio." + exit(1) in the reference)
+  if (inW < m->W || inH < m->H) return fail(SE_B200_ERR_ARG, "Invalid ratio.");
+  if (inW % m->W != 0 || inH % m->H != 0) return fail(SE_B200_ERR_ARG, "Invalid ratio.");
+  if (inW / m->W != inH / m->H) return fail(SE_B200_ERR_ARG, "Invalid ratio.");
+  return SE_B200_OK;
+}
+
+int se_b200_preprocess_depth_host(se_b200_map* m, const uint16_t* depth_mm, int inW, int inH) {
+  REQUIRE_MAP(m);
+  if (!depth_mm) return fail(SE_B200_ERR_ARG, "depth_mm is null");
+  if (int r = check_ratio(m, inW, inH)) return r;
+  DeviceGuard guard(m->device);
+  const size_t bytes = (size_t)inW * inH * sizeof(uint16_t);
+  if (m->depth_mm_capacity < bytes) {
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    cudaFree(m->d_depth_mm); m->d_depth_mm = nullptr; m->depth_mm_capacity = 0;
+    CUDA_TRY(cudaMalloc(&m->d_depth_mm, bytes));
+    m->depth_mm_capacity = bytes;
+  }
+  stage_begin(m, SE_B200_STAGE_PREPROCESS);
+  CUDA_TRY(cudaMemcpyAsync(m->d_depth_mm, depth_mm, bytes, cudaMemcpyHostToDevice, m->stream));
+  if (int r = preprocess_common(m, m->d_depth_mm, inW, inH)) return r;
+  stage_end(m, SE_B200_STAGE_PREPROCESS);
+  return SE_B200_OK;
+}
+
+int se_b200_preprocess_depth_device(se_b200_map* m, const uint16_t* depth_mm_dev, int inW, int inH) {
+  REQUIRE_MAP(m);
+  if (!depth_mm_dev) return fail(SE_B200_ERR_ARG, "depth_mm_dev is null");
+  if (int r = check_ratio(m, inW, inH)) return r;
+  DeviceGuard guard(m->device);
+  stage_begin(m, SE_B200_STAGE_PREPROCESS);
+  if (int r = preprocess_common(m, depth_mm_dev, inW, inH)) return r;
+  stage_end(m, SE_B200_STAGE_PREPROCESS);
+  return SE_B200_OK;
+}
+
+int se_b200_set_depth_m_host(se_b200_map* m, const float* depth_m) {
+  REQUIRE_MAP(m);
+  if (!depth_m) return fail(SE_B200_ERR_ARG, "depth_m is null");
+  DeviceGuard guard(m->device);
+  CUDA_TRY(cudaMemcpyAsync(m->d_depth, depth_m, (size_t)m->W * m->H * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_integrate(se_b200_map* m, const float pose[16], const float k[4], float mu, unsigned frame) {
+  REQUIRE_MAP(m);
+  if (!pose || !k) return fail(SE_B200_ERR_ARG, "pose/k is null");
+  DeviceGuard guard(m->device);
+  return FIELD_DISPATCH(m, integrate_impl<SdfVoxel>(m, pose, k, mu, frame), integrate_impl<OfuVoxel>(m, pose, k, mu, frame));
+}
+
+int se_b200_raycast(se_b200_map* m, const float pose[16], const float k[4], float mu) {
+  REQUIRE_MAP(m);
+  if (!pose || !k) return fail(SE_B200_ERR_ARG, "pose/k is null");
+  DeviceGuard guard(m->device);
+  return FIELD_DISPATCH(m, raycast_impl<SdfVoxel>(m, pose, k, mu), raycast_impl<OfuVoxel>(m, pose, k, mu));
+}
+
+int se_b200_download_vertex_normal(se_b200_map* m, float* vertex, float* normal) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  const size_t bytes = (size_t)m->W * m->H * 3 * sizeof(float);
+  if (vertex) CUDA_TRY(cudaMemcpyAsync(vertex, m->d_vertex, bytes, cudaMemcpyDeviceToHost, m->stream));
+  if (normal) CUDA_TRY(cudaMemcpyAsync(normal, m->d_normal, bytes, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_upload_vertex_normal(se_b200_map* m, const float* vertex, const float* normal) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  const size_t bytes = (size_t)m->W * m->H * 3 * sizeof(float);
+  if (vertex) CUDA_TRY(cudaMemcpyAsync(m->d_vertex, vertex, bytes, cudaMemcpyHostToDevice, m->stream));
+  if (normal) CUDA_TRY(cudaMemcpyAsync(m->d_normal, normal, bytes, cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_render_volume_device(se_b200_map* m, uint8_t* out_dev, const float view_pose[16], const float k[4],
+                                 float mu, float largestep, int reraycast) {
+  REQUIRE_MAP(m);
+  if (!out_dev || !view_pose || !k) return fail(SE_B200_ERR_ARG, "null argument");
+  DeviceGuard guard(m->device);
+  return FIELD_DISPATCH(m, render_volume_impl<SdfVoxel>(m, (uchar4*)out_dev, view_pose, k, mu, largestep, reraycast),
+                        render_volume_impl<OfuVoxel>(m, (uchar4*)out_dev, view_pose, k, mu, largestep, reraycast));
+}
+
+int se_b200_render_volume_host(se_b200_map* m, uint8_t* out, const float view_pose[16], const float k[4],
+                               float mu, float largestep, int reraycast) {
+  REQUIRE_MAP(m);
+  if (!out) return fail(SE_B200_ERR_ARG, "out is null");
+  if (int r = se_b200_render_volume_device(m, (uint8_t*)m->d_rgba, view_pose, k, mu, largestep, reraycast)) return r;
+  DeviceGuard guard(m->device);
+  CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)m->W * m->H * 4, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_render_depth_host(se_b200_map* m, uint8_t* out) {
+  REQUIRE_MAP(m);
+  if (!out) return fail(SE_B200_ERR_ARG, "out is null");
+  DeviceGuard guard(m->device);
+  const int n = m->W * m->H;
+  k_render_depth<<<(n + 255) / 256, 256, 0, m->stream>>>(m->d_rgba, m->d_depth, n, kNearPlane, kFarPlane);
+  if (int r = check_launch(m)) return r;
+  CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_render_track_host(se_b200_map* m, uint8_t* out, const int* track_result, int stride_ints) {
+  REQUIRE_MAP(m);
+  if (!out || !track_result || stride_ints < 1) return fail(SE_B200_ERR_ARG, "bad argument");
+  DeviceGuard guard(m->device);
+  const int n = m->W * m->H;
+  const size_t bytes = (size_t)n * stride_ints * sizeof(int);
+  if (m->track_capacity < bytes) {
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    cudaFree(m->d_track); m->d_track = nullptr; m->track_capacity = 0;
+    CUDA_TRY(cudaMalloc(&m->d_track, bytes));
+    m->track_capacity = bytes;
+  }
+  CUDA_TRY(cudaMemcpyAsync(m->d_track, track_result, bytes, cudaMemcpyHostToDevice, m->stream));
+  k_render_track<<<(n + 255) / 256, 256, 0, m->stream>>>(m->d_rgba, m->d_track, stride_ints, n);
+  if (int r = check_launch(m)) return r;
+  CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_block_count(se_b200_map* m, int* out) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  if (int r = fetch_counters(m)) return r;
+  if (out) *out = std::min(m->h_counters[kCntBlocks], m->max_blocks);
+  return check_pool_error(m);
+}
+int se_b200_node_count(se_b200_map* m, int* out) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  if (int r = fetch_counters(m)) return r;
+  if (out) *out = std::min(m->h_counters[kCntNodes], m->max_nodes);
+  return check_pool_error(m);
+}
+
+int se_b200_download_blocks_sorted(se_b200_map* m, uint64_t* keys, int32_t* coords, uint8_t* active, void* voxels) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  return FIELD_DISPATCH(m, download_blocks_sorted_impl<SdfVoxel>(m, keys, coords, active, voxels),
+                        download_blocks_sorted_impl<OfuVoxel>(m, keys, coords, active, voxels));
+}
+int se_b200_download_nodes_sorted(se_b200_map* m, uint64_t* codes, uint32_t* side, uint8_t* mask, void* values) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  return FIELD_DISPATCH(m, download_nodes_sorted_impl<SdfVoxel>(m, codes, side, mask, values),
+                        download_nodes_sorted_impl<OfuVoxel>(m, codes, side, mask, values));
+}
+
+int se_b200_allocate_keys(se_b200_map* m, const uint64_t* keys, int n) {
+  REQUIRE_MAP(m);
+  if (n < 0 || (n > 0 && !keys)) return fail(SE_B200_ERR_ARG, "bad key list");
+  if (n == 0) return SE_B200_OK;              // the reference would process one stale key here (unique.hpp:51-60)
+  DeviceGuard guard(m->device);
+  // host side: sort + filter_ancestors to find keys[0] of the reference's list (its extra chain)
+  std::vector<unsigned long long> k(keys, keys + n);
+  std::sort(k.begin(), k.end());
+  int e = 0;
+  for (int i = 0; i < n; ++i) { if (key_descendant(k[i], k[e], m->max_level)) k[e] = k[i]; else k[++e] = k[i]; }
+  k.resize(e + 1);
+  if (key_level(k[0]) < m->leaves_level) k.push_back(key_code(k[0]) | (unsigned long long)m->leaves_level);
+  Scratch d;
+  CUDA_TRY(d.alloc(k.size() * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemcpyAsync(d.p, k.data(), k.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, m->stream));
+  const int cnt = (int)k.size();
+  if (m->field == SE_B200_SDF) k_allocate_keys<SdfVoxel><<<(cnt + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (unsigned long long*)d.p, cnt);
+  else k_allocate_keys<OfuVoxel><<<(cnt + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (unsigned long long*)d.p, cnt);
+  if (int r = check_launch(m)) return r;
+  if (int r = fetch_counters(m)) return r;
+  return check_pool_error(m);
+}
+
+int se_b200_query_voxels(se_b200_map* m, const int32_t* xyz, int n, void* out) {
+  REQUIRE_MAP(m);
+  if (n <= 0) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  Scratch dx, dout;
+  CUDA_TRY(dx.alloc((size_t)n * 3 * sizeof(int)));
+  CUDA_TRY(dout.alloc((size_t)n * m->voxel_bytes));
+  CUDA_TRY(cudaMemcpyAsync(dx.p, xyz, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  if (m->field == SE_B200_SDF) k_query_voxels<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (int*)dx.p, n, (SdfVoxel*)dout.p);
+  else k_query_voxels<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (int*)dx.p, n, (OfuVoxel*)dout.p);
+  if (int r = check_launch(m)) return r;
+  CUDA_TRY(cudaMemcpyAsync(out, dout.p, (size_t)n * m->voxel_bytes, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_query_interp(se_b200_map* m, const float* pos, int n, float* out) {
+  REQUIRE_MAP(m);
+  if (n <= 0) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  Scratch dx, dout;
+  CUDA_TRY(dx.alloc((size_t)n * 3 * sizeof(float)));
+  CUDA_TRY(dout.alloc((size_t)n * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(dx.p, pos, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  if (m->field == SE_B200_SDF) k_query_interp<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  else k_query_interp<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  if (int r = check_launch(m)) return r;
+  CUDA_TRY(cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_query_grad(se_b200_map* m, const float* pos, int n, float* out) {
+  REQUIRE_MAP(m);
+  if (n <= 0) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  Scratch dx, dout;
+  CUDA_TRY(dx.alloc((size_t)n * 3 * sizeof(float)));
+  CUDA_TRY(dout.alloc((size_t)n * 3 * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(dx.p, pos, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  if (m->field == SE_B200_SDF) k_query_grad<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  else k_query_grad<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  if (int r = check_launch(m)) return r;
+  CUDA_TRY(cudaMemcpyAsync(out, dout.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_set_voxels(se_b200_map* m, const int32_t* xyz, const void* voxels, int n) {
+  REQUIRE_MAP(m);
+  if (n <= 0) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  Scratch dx, dv;
+  CUDA_TRY(dx.alloc((size_t)n * 3 * sizeof(int)));
+  CUDA_TRY(dv.alloc((size_t)n * m->voxel_bytes));
+  CUDA_TRY(cudaMemcpyAsync(dx.p, xyz, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(dv.p, voxels, (size_t)n * m->voxel_bytes, cudaMemcpyHostToDevice, m->stream));
+  if (m->field == SE_B200_SDF) k_set_voxels<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (int*)dx.p, (SdfVoxel*)dv.p, n);
+  else k_set_voxels<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (int*)dx.p, (OfuVoxel*)dv.p, n);
+  if (int r = check_launch(m)) return r;
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_query_rays(se_b200_map* m, const float* origin_dir, int n, float near_plane, float far_plane,
+                       uint64_t* first_block_key, float* tinfo) {
+  REQUIRE_MAP(m);
+  if (n <= 0) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  Scratch dx, dk, dt;
+  CUDA_TRY(dx.alloc((size_t)n * 6 * sizeof(float)));
+  CUDA_TRY(dk.alloc((size_t)n * sizeof(unsigned long long)));
+  CUDA_TRY(dt.alloc((size_t)n * 3 * sizeof(float)));
+  CUDA_TRY(cudaMemcpyAsync(dx.p, origin_dir, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+  if (m->field == SE_B200_SDF) k_query_ray<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+  else k_query_ray<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+  if (int r = check_launch(m)) return r;
+  if (first_block_key) CUDA_TRY(cudaMemcpyAsync(first_block_key, dk.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+  if (tinfo) CUDA_TRY(cudaMemcpyAsync(tinfo, dt.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_elapsed_ms(se_b200_map* m, int stage, float* ms) {
+  REQUIRE_MAP(m);
+  if (stage < 0 || stage >= SE_B200_NUM_STAGES || !ms) return fail(SE_B200_ERR_ARG, "bad stage");
+  if (!m->ev_valid[stage]) { *ms = 0.f; return SE_B200_OK; }
+  DeviceGuard guard(m->device);
+  CUDA_TRY(cudaEventSynchronize(m->ev_end[stage]));
+  CUDA_TRY(cudaEventElapsedTime(ms, m->ev_begin[stage], m->ev_end[stage]));
+  return SE_B200_OK;
+}
+
+int se_b200_counters(se_b200_map* m, int32_t out[8]) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  if (int r = fetch_counters(m)) return r;
+  for (int i = 0; i < 8; ++i) out[i] = m->h_counters[i];
+  return check_pool_error(m);
+}
+
+int se_b200_launch_count(se_b200_map* m, int64_t* out) {
+  REQUIRE_MAP(m);
+  if (out) *out = m->launches;
+  return SE_B200_OK;
+}
+
+int se_b200_device_image(se_b200_map* m, int which, void** ptr) {
+  REQUIRE_MAP(m);
+  if (!ptr) return fail(SE_B200_ERR_ARG, "ptr is null");
+  switch (which) {
+    case 0: *ptr = m->d_depth; break;
+    case 1: *ptr = m->d_vertex; break;
+    case 2: *ptr = m->d_normal; break;
+    default: return fail(SE_B200_ERR_ARG, "which must be 0..2");
+  }
+  return SE_B200_OK;
+}
+
+}  // extern "C"

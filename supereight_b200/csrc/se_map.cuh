@@ -1,0 +1,321 @@
+// se_map.cuh -- the octree as flat, index-addressed pools in HBM (no host pointers) and the
+// device-side accessors every kernel shares.
+//
+// Layout (DESIGN.md "Data layout in HBM"):
+//   nodes  : SoA, index 0 is the root.   node_child[8n+i] = index of child i (a node index
+//            above the leaves level, a block index at it), kEmpty when absent, kBusy while a
+//            thread is creating it.  node_code / node_side / node_mask / node_value[8n+i]
+//            mirror Node<T>::code_/side_/children_mask_/value_ (se_core/include/se/node.hpp:45-90).
+//   blocks : block_code, block_coord (low corner, voxel units), block_active and
+//            block_data[512 b + x + 8y + 64z] mirror VoxelBlock<T> (node.hpp:92-145).  One
+//            block's payload is one contiguous, 4 KiB (SDF) / 8 KiB (OFusion) aligned run, so a
+//            warp streams it as float4/int4 rows.
+//   counters[kCntNodes/kCntBlocks] are bump allocators (MemoryPool::acquire_block,
+//            se_core/include/se/utils/memory_pool.hpp:69-76); pools are pre-initialised to
+//            initValue() at creation, so allocation never touches the payload.
+//
+// Accessor semantics follow se_core/include/se/octree.hpp (fetch :440-458, get_fine :356-377,
+// interp :541-563 + interpolation/interp_gather.hpp:105-237, grad :652-737).
+#pragma once
+#include "se_math.cuh"
+
+namespace se_b200 {
+
+constexpr int kEmpty = -1;
+constexpr int kBusy = -2;
+
+enum Counter { kCntNodes = 0, kCntBlocks = 1, kCntActive = 2, kCntError = 3, kCntNewBlocksBase = 4, kCntNewNodesBase = 5,
+               kCntKeys = 6, kCntScratch = 7, kNumCounters = 16 };
+enum ErrorBits { kErrBlockPoolFull = 1, kErrNodePoolFull = 2, kErrKeyListFull = 4 };
+
+// ---- field types (se_denseslam/include/se/volume_traits.hpp:41-72) --------------------
+struct SdfVoxel { float x; float y; };                                    // tsdf, weight
+struct __align__(16) OfuVoxel { float x; float pad_; double y; };         // log-odds, timestamp (double, as in the reference)
+
+template <class V> struct FieldTraits;
+template <> struct FieldTraits<SdfVoxel> {
+  static constexpr bool is_sdf = true;
+  SE_HD static SdfVoxel init() { SdfVoxel v; v.x = 1.f; v.y = 0.f; return v; }
+  SE_HD static float empty_x() { return 1.f; }
+};
+template <> struct FieldTraits<OfuVoxel> {
+  static constexpr bool is_sdf = false;
+  SE_HD static OfuVoxel init() { OfuVoxel v; v.x = 0.f; v.pad_ = 0.f; v.y = 0.0; return v; }
+  SE_HD static float empty_x() { return 0.f; }
+};
+
+template <class V> struct MapView {
+  int size;            // voxels per side
+  float dim;           // metres per side
+  int max_level;       // log2(size)
+  int leaves_level;    // max_level - 3
+  int max_nodes, max_blocks;
+  int* node_child;
+  unsigned long long* node_code;
+  unsigned int* node_side;
+  unsigned int* node_mask;
+  V* node_value;
+  unsigned long long* block_code;
+  int4* block_coord;   // x, y, z, unused
+  int* block_active;
+  V* block_data;
+  int* counters;
+};
+
+// ---- device accessors -------------------------------------------------------------------
+#ifdef __CUDACC__
+
+template <class V>
+__device__ __forceinline__ bool in_volume(const MapView<V>& m, int x, int y, int z) {
+  return ((unsigned)x < (unsigned)m.size) & ((unsigned)y < (unsigned)m.size) & ((unsigned)z < (unsigned)m.size);
+}
+
+// Octree::fetch (octree.hpp:440-458); kEmpty when the block is not allocated.  Coordinates
+// outside the volume read as "not allocated" (the reference indexes out of bounds there).
+// Read-only accessors (this one, get_fine, interp, grad) go through the non-coherent cache
+// (__ldg): they are only used by kernels that do not modify the tree.
+template <class V>
+__device__ __forceinline__ int fetch_block(const MapView<V>& m, int x, int y, int z) {
+  if (!in_volume(m, x, y, z)) return kEmpty;
+  int n = 0;
+  for (int edge = m.size >> 1; edge >= kBlockSide; edge >>= 1) {
+    const int slot = ((x & edge) != 0) | (((y & edge) != 0) << 1) | (((z & edge) != 0) << 2);
+    n = __ldg(m.node_child + 8 * n + slot);
+    if (n < 0) return kEmpty;
+  }
+  return n;
+}
+
+// Octree::fetch_octant (octree.hpp:460-478): node/block at `depth`, is_block tells which pool.
+template <class V>
+__device__ __forceinline__ int fetch_octant(const MapView<V>& m, int x, int y, int z, int depth, bool& is_block) {
+  is_block = false;
+  if (!in_volume(m, x, y, z)) return kEmpty;
+  int n = 0;
+  int d = 1;
+  for (int edge = m.size >> 1; edge >= kBlockSide && d <= depth; edge >>= 1, ++d) {
+    const int slot = ((x & edge) != 0) | (((y & edge) != 0) << 1) | (((z & edge) != 0) << 2);
+    n = __ldcg(m.node_child + 8 * n + slot);
+    if (n < 0) return kEmpty;
+    is_block = (edge == kBlockSide);
+  }
+  return n;
+}
+
+// A one-entry per-thread cache of the last block looked up: successive samples of a ray, the
+// 8 corners of an interpolation and the 32 voxels of a gradient mostly fall in one block, so
+// this removes most root-to-leaf descents without changing any result.
+struct BlockCache {
+  int bx, by, bz, idx;
+  __device__ __forceinline__ BlockCache() : bx(-1), by(-1), bz(-1), idx(kEmpty) {}
+};
+template <class V>
+__device__ __forceinline__ int fetch_block_cached(const MapView<V>& m, BlockCache& c, int x, int y, int z) {
+  const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+  if (bx == c.bx && by == c.by && bz == c.bz) return c.idx;
+  const int idx = fetch_block(m, x, y, z);
+  if (in_volume(m, x, y, z)) { c.bx = bx; c.by = by; c.bz = bz; c.idx = idx; }
+  return idx;
+}
+
+__device__ __forceinline__ float load_x(const SdfVoxel* p) { return __ldg(&p->x); }
+__device__ __forceinline__ float load_x(const OfuVoxel* p) { return __ldg(&p->x); }
+__device__ __forceinline__ SdfVoxel load_voxel(const SdfVoxel* p) {
+  const float2 t = __ldg(reinterpret_cast<const float2*>(p)); SdfVoxel v; v.x = t.x; v.y = t.y; return v;
+}
+__device__ __forceinline__ OfuVoxel load_voxel(const OfuVoxel* p) {
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  OfuVoxel v; v.x = __int_as_float((int)(__double_as_longlong(t.x) & 0xffffffffll)); v.pad_ = 0.f; v.y = t.y; return v;
+}
+
+template <class V>
+__device__ __forceinline__ int voxel_offset(int x, int y, int z) { return (x & 7) | ((y & 7) << 3) | ((z & 7) << 6); }
+
+// Octree::get_fine (octree.hpp:356-377): initValue() where nothing is allocated
+template <class V>
+__device__ __forceinline__ V get_fine(const MapView<V>& m, BlockCache& c, int x, int y, int z) {
+  const int b = fetch_block_cached(m, c, x, y, z);
+  if (b < 0) return FieldTraits<V>::init();
+  return load_voxel(m.block_data + (size_t)b * kBlockVoxels + voxel_offset<V>(x, y, z));
+}
+template <class V>
+__device__ __forceinline__ float get_fine_x(const MapView<V>& m, BlockCache& c, int x, int y, int z) {
+  const int b = fetch_block_cached(m, c, x, y, z);
+  if (b < 0) return FieldTraits<V>::init().x;
+  return load_x(m.block_data + (size_t)b * kBlockVoxels + voxel_offset<V>(x, y, z));
+}
+
+// gather_points (interp_gather.hpp:105-237): the 8 corners are grouped by the block they fall
+// in; one fetch per group; a missing block reads empty() in cases 0..6 and initValue() in the
+// all-axes-crossing case 7.
+template <class V>
+__device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int bx, int by, int bz, float p[8]) {
+  const unsigned cross = ((unsigned)((bx & 7) == 7) << 2) | ((unsigned)((by & 7) == 7) << 1) | (unsigned)((bz & 7) == 7);
+  if (cross == 0u) {
+    const int b = fetch_block_cached(m, c, bx, by, bz);
+    if (b < 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = FieldTraits<V>::empty_x();
+    } else {
+      const V* base = m.block_data + (size_t)b * kBlockVoxels + voxel_offset<V>(bx, by, bz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p[i] = load_x(base + (i & 1) + ((i & 2) << 2) + ((i & 4) << 4));
+    }
+    return;
+  }
+  const float missing = (cross == 7u) ? FieldTraits<V>::init().x : FieldTraits<V>::empty_x();
+  // one fetch per group of corners sharing a block: groups are the subsets g of the crossing axes
+  for (unsigned g = cross;; g = (g - 1u) & cross) {
+    const int gx = (int)((g >> 2) & 1u), gy = (int)((g >> 1) & 1u), gz = (int)(g & 1u);
+    const int b = fetch_block_cached(m, c, bx + gx, by + gy, bz + gz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
+      const unsigned cb = ((unsigned)ox << 2) | ((unsigned)oy << 1) | (unsigned)oz;
+      if ((cb & cross) == g)
+        p[i] = (b < 0) ? missing : load_x(m.block_data + (size_t)b * kBlockVoxels + voxel_offset<V>(bx + ox, by + oy, bz + oz));
+    }
+    if (g == 0u) break;
+  }
+}
+
+// Octree::interp (octree.hpp:541-563), pos in voxel units
+template <class V>
+__device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c, V3 pos) {
+  const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
+  const float fx = pos.x - flx, fy = pos.y - fly, fz = pos.z - flz;
+  const int bx = max((int)flx, 0), by = max((int)fly, 0), bz = max((int)flz, 0);
+  float p[8];
+  gather_points(m, c, bx, by, bz, p);
+  return (((p[0] * (1 - fx) + p[1] * fx) * (1 - fy)
+         + (p[2] * (1 - fx) + p[3] * fx) * fy) * (1 - fz)
+        + ((p[4] * (1 - fx) + p[5] * fx) * (1 - fy)
+         + (p[6] * (1 - fx) + p[7] * fx) * fy) * fz);
+}
+
+// Octree::grad(pos, select) (octree.hpp:652-737): central differences blended trilinearly
+template <class V>
+__device__ __forceinline__ V3 grad_field(const MapView<V>& m, BlockCache& c, V3 pos) {
+  const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
+  const int b0 = (int)flx, b1 = (int)fly, b2 = (int)flz;
+  const float wx1 = pos.x - flx, wy1 = pos.y - fly, wz1 = pos.z - flz;
+  const float wx0 = 1 - wx1, wy0 = 1 - wy1, wz0 = 1 - wz1;
+  const int hi = m.size - 1;
+  // per axis: ll = max(b-1,0), lu = max(b,0), ul = min(b+1,hi), uu = min(b+2,hi)
+  const int x_ll = max(b0 - 1, 0), x_lu = max(b0, 0), x_ul = min(b0 + 1, hi), x_uu = min(b0 + 2, hi);
+  const int y_ll = max(b1 - 1, 0), y_lu = max(b1, 0), y_ul = min(b1 + 1, hi), y_uu = min(b1 + 2, hi);
+  const int z_ll = max(b2 - 1, 0), z_lu = max(b2, 0), z_ul = min(b2 + 1, hi), z_uu = min(b2 + 2, hi);
+  // the 32 distinct samples: 4 x-values at the 4 (y,z) of the inner square, etc.
+#define G(X, Y, Z) get_fine_x(m, c, (X), (Y), (Z))
+  V3 r;
+  {
+    const float t00 = (G(x_ul, y_lu, z_lu) - G(x_ll, y_lu, z_lu)) * wx0 + (G(x_uu, y_lu, z_lu) - G(x_lu, y_lu, z_lu)) * wx1;
+    const float t10 = (G(x_ul, y_ul, z_lu) - G(x_ll, y_ul, z_lu)) * wx0 + (G(x_uu, y_ul, z_lu) - G(x_lu, y_ul, z_lu)) * wx1;
+    const float t01 = (G(x_ul, y_lu, z_ul) - G(x_ll, y_lu, z_ul)) * wx0 + (G(x_uu, y_lu, z_ul) - G(x_lu, y_lu, z_ul)) * wx1;
+    const float t11 = (G(x_ul, y_ul, z_ul) - G(x_ll, y_ul, z_ul)) * wx0 + (G(x_uu, y_ul, z_ul) - G(x_lu, y_ul, z_ul)) * wx1;
+    r.x = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
+  }
+  {
+    const float t00 = (G(x_lu, y_ul, z_lu) - G(x_lu, y_ll, z_lu)) * wx0 + (G(x_ul, y_ul, z_lu) - G(x_ul, y_ll, z_lu)) * wx1;
+    const float t10 = (G(x_lu, y_uu, z_lu) - G(x_lu, y_lu, z_lu)) * wx0 + (G(x_ul, y_uu, z_lu) - G(x_ul, y_lu, z_lu)) * wx1;
+    const float t01 = (G(x_lu, y_ul, z_ul) - G(x_lu, y_ll, z_ul)) * wx0 + (G(x_ul, y_ul, z_ul) - G(x_ul, y_ll, z_ul)) * wx1;
+    const float t11 = (G(x_lu, y_uu, z_ul) - G(x_lu, y_lu, z_ul)) * wx0 + (G(x_ul, y_uu, z_ul) - G(x_ul, y_lu, z_ul)) * wx1;
+    r.y = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
+  }
+  {
+    const float t00 = (G(x_lu, y_lu, z_ul) - G(x_lu, y_lu, z_ll)) * wx0 + (G(x_ul, y_lu, z_ul) - G(x_ul, y_lu, z_ll)) * wx1;
+    const float t10 = (G(x_lu, y_ul, z_ul) - G(x_lu, y_ul, z_ll)) * wx0 + (G(x_ul, y_ul, z_ul) - G(x_ul, y_ul, z_ll)) * wx1;
+    const float t01 = (G(x_lu, y_lu, z_uu) - G(x_lu, y_lu, z_lu)) * wx0 + (G(x_ul, y_lu, z_uu) - G(x_ul, y_lu, z_lu)) * wx1;
+    const float t11 = (G(x_lu, y_ul, z_uu) - G(x_lu, y_ul, z_lu)) * wx0 + (G(x_ul, y_ul, z_uu) - G(x_ul, y_ul, z_lu)) * wx1;
+    r.z = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
+  }
+#undef G
+  const float s = (0.5f * m.dim) / (float)m.size;
+  return v3(s * r.x, s * r.y, s * r.z);
+}
+
+// VolumeTemplate::{get,interp,grad} (se_denseslam/include/se/continuous/volume_template.hpp:77-102):
+// metres -> voxels by size/dim; get truncates toward zero, interp/grad floor.
+template <class V>
+__device__ __forceinline__ V vol_get(const MapView<V>& m, BlockCache& c, V3 p) {
+  const float inv = (float)m.size / m.dim;
+  return get_fine(m, c, (int)(inv * p.x), (int)(inv * p.y), (int)(inv * p.z));
+}
+template <class V>
+__device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, V3 p) {
+  const float inv = (float)m.size / m.dim;
+  return interp_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
+}
+template <class V>
+__device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, V3 p) {
+  const float inv = (float)m.size / m.dim;
+  return grad_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
+}
+
+// ---- insertion -----------------------------------------------------------------------------
+// Find-or-create the octant `code` at `target_level`, creating the path from the root:
+// Octree::allocate_level's walk (octree.hpp:819-856) done by whoever gets there first.
+// A missing child slot is claimed with atomicCAS(kEmpty -> kBusy); the winner takes an index
+// from the bump allocator, fills the metadata, and publishes the index with a fence; losers
+// re-read the slot until it is published.  The winner never waits on anyone, so the scheme is
+// starvation-free under independent thread scheduling.
+// Returns the node/block index, or kEmpty when a pool is exhausted (error bit set);
+// created_target tells whether this call created the octant at target_level itself.
+template <class V>
+__device__ __forceinline__ int find_or_create(const MapView<V>& m, unsigned long long code, int target_level, bool& created_target) {
+  created_target = false;
+  int n = 0;
+  int edge = m.size >> 1;
+  for (int level = 1; level <= target_level; ++level, edge >>= 1) {
+    const int slot = key_child_id(code, level, m.max_level);
+    int* p = m.node_child + 8 * n + slot;
+    int c = __ldcg(p);
+    while (c < 0) {
+      if (c == kEmpty) {
+        const int old = atomicCAS(p, kEmpty, kBusy);
+        if (old == kEmpty) {
+          const unsigned long long prefix = code & level_mask(kMaxBits - m.max_level + level - 1);
+          int idx;
+          if (level == m.leaves_level) {
+            idx = atomicAdd(m.counters + kCntBlocks, 1);
+            if (idx >= m.max_blocks) {
+              atomicSub(m.counters + kCntBlocks, 1);
+              atomicOr(m.counters + kCntError, kErrBlockPoolFull);
+              atomicExch(p, kEmpty);
+              return kEmpty;
+            }
+            int x, y, z;
+            morton_decode(prefix, x, y, z);
+            m.block_code[idx] = prefix | (unsigned long long)level;
+            m.block_coord[idx] = make_int4(x, y, z, 0);
+            m.block_active[idx] = 1;
+          } else {
+            idx = atomicAdd(m.counters + kCntNodes, 1);
+            if (idx >= m.max_nodes) {
+              atomicSub(m.counters + kCntNodes, 1);
+              atomicOr(m.counters + kCntError, kErrNodePoolFull);
+              atomicExch(p, kEmpty);
+              return kEmpty;
+            }
+            m.node_code[idx] = prefix | (unsigned long long)level;
+            m.node_side[idx] = (unsigned)edge;
+          }
+          if (level == target_level) created_target = true;
+          atomicOr(m.node_mask + n, 1u << slot);
+          __threadfence();
+          atomicExch(p, idx);
+          c = idx;
+        } else {
+          c = old;
+        }
+      } else {
+        c = *((volatile int*)p);     // kBusy: someone is publishing this slot
+      }
+    }
+    n = c;
+  }
+  return n;
+}
+
+#endif  // __CUDACC__
+}  // namespace se_b200
