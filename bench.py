@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the per-frame dense-SLAM hot path (BASELINE.json `metric`).
+
+A "step" is one frame of a synthetic 640x480 depth stream through the whole hot path:
+mm2meters -> block allocation -> TSDF integration (+ node update) -> raycast -> renderVolume (reuse
+path), i.e. DenseSLAMSystem::{preprocessing, integration, raycasting, renderVolume} with poses
+supplied (tracking excluded on both sides).
+
+  python bench.py [--gpus N --steps K --warmup W]        our CUDA path (one process per GPU)
+  python bench.py --impl reference ...                   the reference algorithm on the host cores
+                                                         (CPU oracle port, OpenMP)
+
+N>1 (launched by torch.distributed.run): one independent sequence + map per GPU ("replicas only",
+SURVEY.md 8(e)); NCCL is used for the barrier and to gather timings, nothing else.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec (integrate+raycast) 640x480 -> 512^3 TSDF octree"
+UNIT = "frames/s"
+WORKLOADS = {
+    # BASELINE.json configs[1]: synthetic planar sweep, SDF 512^3 -- the configuration the metric is quoted on
+    "planar_sweep_sdf512": dict(field=0, size=512, dim=4.8, mu=0.1, scene="plane", W=640, H=480),
+    # configs[2]/[3]: selectable for profiling runs, not bench lines
+    "box_room_ofusion1024": dict(field=1, size=1024, dim=4.8, mu=0.008, scene="room", W=640, H=480),
+    "box_room_sdf2048": dict(field=0, size=2048, dim=4.096, mu=0.1, scene="room", W=640, H=480, max_blocks=1 << 20),
+    "planar_sweep_sdf256_small": dict(field=0, size=256, dim=4.8, mu=0.1, scene="plane", W=160, H=120),
+}
+K_CAM = (481.2, 480.0, 320.0, 240.0)
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def camera_for(cfg):
+    s = cfg["W"] / 640.0
+    return tuple(v * s for v in K_CAM)
+
+
+def make_frames(cfg, n, seed):
+    from supereight_b200 import synth
+    gen = synth.planar_sweep if cfg["scene"] == "plane" else synth.box_room
+    k = camera_for(cfg)
+    depth = np.empty((n, cfg["H"], cfg["W"]), np.uint16)
+    poses = np.empty((n, 4, 4), np.float32)
+    for f in range(n):
+        depth[f], poses[f] = gen(f, cfg["dim"], cfg["W"], cfg["H"], k, noise_mm=2.0, dropout=0.01, seed=seed)
+    return depth, poses, k
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(cfg, counters, samples):
+    """SURVEY.md 8(d) / BASELINE.md section 4, per frame, per stage."""
+    vb = 8 if cfg["field"] == 0 else 16
+    bb = 512 * vb
+    px = cfg["W"] * cfg["H"]
+    new_blocks = counters["blocks"] - counters["blocks_before"]
+    new_nodes = counters["nodes"] - counters["nodes_before"]
+    unique_keys = new_blocks if cfg["field"] == 0 else counters["requests"]
+    return {
+        "alloc": px * 4 + new_blocks * bb + new_nodes * (8 * 4 + 8 + 8 * vb) + unique_keys * 8,
+        "fuse": counters["active"] * (2 * bb + 16) + counters["nodes"] * 8 * vb * 2 + px * 4,
+        "raycast": samples["n_get"] * vb + samples["n_interp"] * 8 * vb + samples["n_grad"] * 32 * vb + px * 24,
+        "render": px * (24 + 4),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference algorithm (oracle port, OpenMP) on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_cpu(cfg, depth, poses, k, warmup, steps, budget_s=25.0):
+    """Times the oracle (oracle/_build/liboracle_fast.so: g++ -O3 -march=x86-64-v3 -fopenmp) over the same
+    frames.  The thread count is calibrated (the reference's alloc pass writes block->active from every
+    ray, which scales badly across sockets), the best one is used and reported."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    lib = oracle_lib.load("fast")
+    ncpu = os.cpu_count() or 1
+    o = oracle_lib.Oracle(cfg["field"], cfg["size"], cfg["dim"], cfg["W"], cfg["H"], kind="fast")
+    mu = cfg["mu"]
+
+    def frame(f):
+        o.preprocess(depth[f]); o.integrate(poses[f], k, mu, f); o.raycast(poses[f], k, mu)
+        o.render_volume(poses[f], k, mu, 0.75 * mu, False)
+
+    t_start = time.perf_counter()
+    f = 0
+    n_frames = len(depth)
+    for _ in range(min(max(warmup, 1), 3)):           # first frames allocate most of the map
+        frame(f % n_frames); f += 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        lib.seo_set_omp_threads(c)
+        frame(f % n_frames); f += 1                    # settle
+        t0 = time.perf_counter()
+        for _ in range(2):
+            frame(f % n_frames); f += 1
+        dt = (time.perf_counter() - t0) / 2
+        if dt < best_t:
+            best, best_t = c, dt
+    lib.seo_set_omp_threads(best)
+    for _ in range(max(0, warmup - 3)):
+        if time.perf_counter() - t_start > budget_s * 0.4:
+            break
+        frame(f % n_frames); f += 1
+    done, t0 = 0, time.perf_counter()
+    while done < steps and (time.perf_counter() - t0) < budget_s * 0.6:
+        frame(f % n_frames); f += 1; done += 1
+    dt = time.perf_counter() - t0
+    fps = done / dt if dt > 0 else 0.0
+    return dict(value=fps, unit=UNIT, cores=best, kind="port",
+                sample=f"{done} frames of the same stream after warm-up, oracle port with OpenMP ({best} of {ncpu} host threads, best of {cands})",
+                ms_per_step=1e3 * dt / max(done, 1), steps=done)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from supereight_b200 import Map
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H, mu = cfg["W"], cfg["H"], cfg["mu"]
+    steps, warmup = args.steps, max(args.warmup, 3)
+    n_frames = warmup + steps
+    depth, poses, k = make_frames(cfg, n_frames, seed=rank)       # one independent sequence per GPU
+    largestep = 0.75 * mu
+
+    def new_map():
+        m = Map(cfg["field"], cfg["size"], cfg["dim"], W, H, max_blocks=cfg.get("max_blocks", 0), device=local_rank)
+        m.set_stream(torch.cuda.current_stream().cuda_stream)
+        return m
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    d_depth = torch.from_numpy(depth.view(np.int16)).to(dev)         # the stream, resident in HBM
+    d_rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+    stages = ("alloc", "fuse", "raycast", "render")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM, device-side outputs ----------------
+    m = new_map()
+
+    def step_resident(f):
+        m.preprocess_device_ptr(d_depth[f].data_ptr(), W, H)
+        m.integrate(poses[f], k, mu, f)
+        m.raycast(poses[f], k, mu)
+        m.render_volume_device_ptr(d_rgba.data_ptr(), poses[f], k, mu, largestep, False)
+
+    for f in range(warmup):
+        flush.zero_(); step_resident(f)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stage_ms = {s: 0.0 for s in stages}
+    launches0 = m.launch_count()
+    wall0 = time.perf_counter()
+    for i in range(steps):
+        f = warmup + i
+        flush.zero_()                      # L2 flush between timed steps (outside the event pair)
+        ev0[i].record(); step_resident(f); ev1[i].record()
+        for s in stages:                   # per-kernel device times of this step (CUDA events on the same stream)
+            stage_ms[s] += m.elapsed_ms(s)
+    barrier()
+    wall = time.perf_counter() - wall0
+    gpu_launches = m.launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    counters = m.counters()
+    samples = m.raycast_count_samples(poses[n_frames - 1], k, mu)
+    m.close()
+
+    # ---------------- e2e: through the C ABI with HOST buffers (pinned), H2D + D2H inside ----------------
+    m = new_map()
+    h_depth = torch.from_numpy(depth.view(np.int16)).pin_memory()
+    h_rgba = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+
+    def step_host(f):
+        m.preprocess_host_ptr(h_depth[f].data_ptr(), W, H)          # cudaMemcpyAsync H2D + mm2meters
+        m.integrate(poses[f], k, mu, f)
+        m.raycast(poses[f], k, mu)
+        m.render_volume_host_ptr(h_rgba.data_ptr(), poses[f], k, mu, largestep, False)   # D2H + sync
+
+    for f in range(warmup):
+        flush.zero_(); step_host(f)
+    barrier()
+    e2e_s = 0.0
+    for i in range(steps):
+        flush.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); step_host(warmup + i); e2e_s += time.perf_counter() - t0
+    barrier()
+    checksum = int(h_rgba.numpy().astype(np.uint64).sum())
+    m.close()
+
+    # ---------------- aggregate: max over ranks ----------------
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    result = None
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        ab = algorithmic_bytes(cfg, counters, samples)
+        kernels = {}
+        for s in stages:
+            ms = stage_ms[s] / steps
+            gbs = ab[s] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            kernels[s] = {"ms": round(ms, 5), "algorithmic_bytes": int(ab[s]), "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        dom = max(stages, key=lambda s: kernels[s]["ms"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+            except Exception:
+                traffic = None
+        frame_bytes = sum(ab.values())
+        frame_ms = sum(kernels[s]["ms"] for s in stages)
+        result = {
+            "metric": METRIC, "value": round(world * steps / (total_ms_max * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(total_ms_max / steps, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "field": "SDF" if cfg["field"] == 0 else "OFusion", "volume": f"{cfg['size']}^3 @ {cfg['dim']} m",
+                       "image": f"{W}x{H}", "mu": mu, "scene": cfg["scene"], "noise_mm": 2.0, "dropout": 0.01,
+                       "stages": "mm2meters+alloc+integrate+raycast+renderVolume(reuse)", "poses": "supplied (no tracking)",
+                       "parallelism": f"replicas x{world} (one map per GPU)", "l2": "flushed between timed steps (256 MiB write)",
+                       "blocks": counters["blocks"], "active_blocks": counters["active"], "nodes": counters["nodes"]},
+            "e2e": {"value": round(world * steps / (e2e_ms_max * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": W * H * 2,
+                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(e2e_ms_max / steps, 5), "result_checksum": checksum},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                         "frame": {"algorithmic_bytes": int(frame_bytes), "achieved_gbs": round(frame_bytes / (frame_ms * 1e-3) / 1e9, 1),
+                                   "frac": round(frame_bytes / (frame_ms * 1e-3) / 1e9 / peak, 4)},
+                         "kernels": kernels},
+            "wall_s_timed_region": round(wall, 3),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            result["cpu_baseline"] = run_cpu(cfg, depth, poses, k, warmup=min(warmup, 5), steps=min(steps, 40), budget_s=25.0)
+            result["cpu_baseline"].pop("ms_per_step", None); result["cpu_baseline"].pop("steps", None)
+            result["cpu_baseline"]["value"] = round(result["cpu_baseline"]["value"], 3)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="planar_sweep_sdf512", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        # The reference's own CPU implementation of the path.  The real supereight cannot be compiled here
+        # (Eigen3/Sophus absent), so this times the line-faithful oracle port with OpenMP on the
+        # host cores.  Rank 0 alone works; the other ranks exit 0.
+        if rank != 0:
+            return
+        warmup = max(args.warmup, 3)
+        n = min(warmup + args.steps, 64)
+        depth, poses, k = make_frames(cfg, n, seed=0)
+        r = run_cpu(cfg, depth, poses, k, warmup=warmup, steps=args.steps, budget_s=150.0)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "field": "SDF" if cfg["field"] == 0 else "OFusion", "volume": f"{cfg['size']}^3 @ {cfg['dim']} m",
+                       "image": f"{cfg['W']}x{cfg['H']}", "mu": cfg["mu"], "scene": cfg["scene"],
+                       "stages": "mm2meters+alloc+integrate+raycast+renderVolume(reuse)", "poses": "supplied (no tracking)"},
+            "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    result = run_gpu(args, cfg, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,9 @@ typedef struct { float x; float pad_; double y; } se_b200_ofusion_voxel; /* log-
 
 const char* se_b200_last_error(void);
 int se_b200_device_count(void);
+/* the 1000-entry B-spline table the OFusion update samples (se_denseslam/src/bfusion/bspline_lookup.cc:36-37),
+ * as uploaded to constant memory; host-side, needs no device */
+int se_b200_bspline_lut(float out[1000]);
 
 /* ---- lifetime --------------------------------------------------------------------------
  * Replaces se::Octree<FieldType>::init (se_core/include/se/octree.hpp:411-421) and the image
@@ -79,6 +82,10 @@ int se_b200_integrate(se_b200_map* map, const float pose[16], const float k[4], 
  * voxel, largestep = one block (DenseSLAMSystem.cpp:197-200).  Vertex and normal maps stay on
  * the device (W*H*3 floats each, row-major, as se::Image<Eigen::Vector3f>). */
 int se_b200_raycast(se_b200_map* map, const float pose[16], const float k[4], float mu);
+/* same raycast, additionally counting the field samples it takes: samples[0] = VolumeTemplate::get,
+ * [1] = interp (8 voxels each), [2] = grad (32 distinct voxels each) -- the inputs of the
+ * algorithmic-bytes figure of SURVEY.md 8(d).  Measurement only. */
+int se_b200_raycast_count_samples(se_b200_map* map, const float pose[16], const float k[4], float mu, uint64_t samples[3]);
 int se_b200_download_vertex_normal(se_b200_map* map, float* vertex, float* normal);   /* either may be NULL */
 int se_b200_upload_vertex_normal(se_b200_map* map, const float* vertex, const float* normal);
 
@@ -87,7 +94,7 @@ int se_b200_upload_vertex_normal(se_b200_map* map, const float* vertex, const fl
  * the reference (benchmark.cpp:90-97).  reraycast != 0 is the reference's `render` flag (view
  * pose differs from the raycast pose: cast again from the volume entry with far plane 8 m);
  * 0 shades the stored vertex/normal maps.  light = translation of view_pose.
- * track_result: W*H ints `stride_ints` apart (TrackData::result, commons.h:228-232 -> stride 8). */
+ * track_result: W*H ints `stride_ints` apart (TrackData::result, commons.h:249-253 -> stride 8). */
 int se_b200_render_volume_host(se_b200_map* map, uint8_t* out, const float view_pose[16], const float k[4],
                                float mu, float largestep, int reraycast);
 int se_b200_render_volume_device(se_b200_map* map, uint8_t* out_dev, const float view_pose[16], const float k[4],

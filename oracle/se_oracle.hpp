@@ -686,16 +686,16 @@ static inline V4 raycast_field(const Octree<OFusion>& vol, V3 origin, V3 directi
 
 // ----------------------------------------------------------------------------
 // a11: OFusion B-spline machinery.  bfusion/mapping_impl.hpp:94-155, bspline_lookup.cc:36-37
-// The 1000-entry table is regenerated from the closed form it samples (bspline() at
-// t = -3 + 6 i / 999, evaluated in float); tests/golden holds a checksum of the
-// reference table to pin it.
+// The 1000-entry table is regenerated from the closed form it samples: bspline() at
+// t = -3 + 6 i / 999 evaluated in double and rounded to float reproduces the reference's
+// printed table bit for bit (tests/golden/bspline_lut.sha256 pins it).
 // ----------------------------------------------------------------------------
-static inline float bspline_closed(float t) {            // mapping_impl.hpp:94-106
-  float value = 0.f;
-  if (t >= -3.0f && t <= -1.0f) value = (float)(std::pow((double)(3 + t), 3) / 48.0f);
-  else if (t > -1 && t <= 1) value = 0.5f + (t * (3 + t) * (3 - t)) / 24.f;
-  else if (t > 1 && t <= 3) value = (float)(1 - std::pow((double)(3 - t), 3) / 48.f);
-  else if (t > 3) value = 1.f;
+static inline double bspline_closed(double t) {          // mapping_impl.hpp:94-106, in double
+  double value = 0.0;
+  if (t >= -3.0 && t <= -1.0) value = std::pow(3 + t, 3) / 48.0;
+  else if (t > -1 && t <= 1) value = 0.5 + (t * (3 + t) * (3 - t)) / 24.0;
+  else if (t > 1 && t <= 3) value = 1 - std::pow(3 - t, 3) / 48.0;
+  else if (t > 3) value = 1.0;
   return value;
 }
 struct BsplineLut {
@@ -1097,8 +1097,8 @@ static inline void render_track(uint8_t* out, const int* result, int stride_ints
 
 inline BsplineLut::BsplineLut() {
   for (int i = 0; i < 1000; ++i) {
-    const float t = -3.f + 6.f * (float)i / 999.f;
-    v[i] = bspline_closed(t);
+    const double t = -3.0 + 6.0 * (double)i / 999.0;
+    v[i] = (float)bspline_closed(t);
   }
 }
 

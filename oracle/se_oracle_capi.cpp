@@ -171,3 +171,15 @@ void seo_get_counters(void* h, uint64_t out[9]) {
 }
 
 }  // extern "C"
+
+// vectorised checks used by the known-answer tests (a scalar ctypes call per voxel would be too slow)
+extern "C" long long seo_morton_roundtrip_mismatches(int x0, int x1, int y0, int y1, int z0, int z1) {
+  long long bad = 0;
+  for (int z = z0; z < z1; ++z)
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const V3i v = morton_decode(morton_encode((uint64_t)x, (uint64_t)y, (uint64_t)z));
+        bad += (v.x != x) | (v.y != y) | (v.z != z);
+      }
+  return bad;
+}

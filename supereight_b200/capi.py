@@ -17,9 +17,9 @@ _lib = None
 
 # every symbol include/se_b200.h declares (tests check that the library exports them all)
 EXPORTS = (
-    "se_b200_last_error", "se_b200_device_count", "se_b200_create", "se_b200_destroy", "se_b200_set_stream",
+    "se_b200_last_error", "se_b200_device_count", "se_b200_bspline_lut", "se_b200_create", "se_b200_destroy", "se_b200_set_stream",
     "se_b200_sync", "se_b200_preprocess_depth_host", "se_b200_preprocess_depth_device", "se_b200_set_depth_m_host",
-    "se_b200_integrate", "se_b200_raycast", "se_b200_download_vertex_normal", "se_b200_upload_vertex_normal",
+    "se_b200_integrate", "se_b200_raycast", "se_b200_raycast_count_samples", "se_b200_download_vertex_normal", "se_b200_upload_vertex_normal",
     "se_b200_render_volume_host", "se_b200_render_volume_device", "se_b200_render_depth_host",
     "se_b200_render_track_host", "se_b200_block_count", "se_b200_node_count", "se_b200_download_blocks_sorted",
     "se_b200_download_nodes_sorted", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
@@ -57,6 +57,7 @@ def load_library():
     lib.se_b200_set_depth_m_host.argtypes = [vp, vp]
     lib.se_b200_integrate.argtypes = [vp, vp, vp, f32, u32]
     lib.se_b200_raycast.argtypes = [vp, vp, vp, f32]
+    lib.se_b200_raycast_count_samples.argtypes = [vp, vp, vp, f32, vp]
     lib.se_b200_download_vertex_normal.argtypes = [vp, vp, vp]
     lib.se_b200_upload_vertex_normal.argtypes = [vp, vp, vp]
     lib.se_b200_render_volume_host.argtypes = [vp, vp, vp, vp, f32, f32, i32]
@@ -148,6 +149,12 @@ class Map:
     def raycast(self, pose, k, mu):
         p, kk = _f32(pose, 16), _f32(k, 4)
         self._check(self.lib.se_b200_raycast(self.h, _ptr(p), _ptr(kk), mu))
+
+    def raycast_count_samples(self, pose, k, mu):
+        p, kk = _f32(pose, 16), _f32(k, 4)
+        out = np.zeros(3, np.uint64)
+        self._check(self.lib.se_b200_raycast_count_samples(self.h, _ptr(p), _ptr(kk), mu, _ptr(out)))
+        return dict(n_get=int(out[0]), n_interp=int(out[1]), n_grad=int(out[2]))
 
     def vertex_normal(self):
         v = np.empty((self.H, self.W, 3), np.float32)

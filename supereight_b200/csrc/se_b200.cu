@@ -105,14 +105,18 @@ void stage_begin(se_b200_map* m, int s) { cudaEventRecord(m->ev_begin[s], m->str
 void stage_end(se_b200_map* m, int s) { cudaEventRecord(m->ev_end[s], m->stream); m->ev_valid[s] = true; }
 
 // B-spline table of bfusion/bspline_lookup.cc:36-37, regenerated from the closed form it samples
-// (mapping_impl.hpp:94-106) at t = -3 + 6 i / 999; tests pin it against a checksum of the original.
-float bspline_closed(float t) {
-  float value = 0.f;
-  if (t >= -3.0f && t <= -1.0f) value = (float)(std::pow((double)(3 + t), 3) / 48.0f);
-  else if (t > -1 && t <= 1) value = 0.5f + (t * (3 + t) * (3 - t)) / 24.f;
-  else if (t > 1 && t <= 3) value = (float)(1 - std::pow((double)(3 - t), 3) / 48.f);
-  else if (t > 3) value = 1.f;
-  return value;
+// (mapping_impl.hpp:94-106): evaluated in double at t = -3 + 6 i / 999 and rounded to float it
+// reproduces the reference's printed table bit for bit (tests/test_bspline_lut.py pins the checksum).
+void make_bspline_lut(float lut[1000]) {
+  for (int i = 0; i < 1000; ++i) {
+    const double t = -3.0 + 6.0 * (double)i / 999.0;
+    double value = 0.0;
+    if (t >= -3.0 && t <= -1.0) value = std::pow(3 + t, 3) / 48.0;
+    else if (t > -1 && t <= 1) value = 0.5 + (t * (3 + t) * (3 - t)) / 24.0;
+    else if (t > 1 && t <= 3) value = 1 - std::pow(3 - t, 3) / 48.0;
+    else if (t > 3) value = 1.0;
+    lut[i] = (float)value;
+  }
 }
 
 int pixel_tile_blocks(int W, int H, int threads) {
@@ -179,10 +183,8 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
 
   // counters: remember the pool sizes before the frame, clear the per-frame ones
   stage_begin(m, SE_B200_STAGE_ALLOC);
-  CUDA_TRY(cudaMemcpyAsync(m->p.counters + kCntNewBlocksBase, m->p.counters + kCntBlocks, sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
-  CUDA_TRY(cudaMemcpyAsync(m->p.counters + kCntNewNodesBase, m->p.counters + kCntNodes, sizeof(int), cudaMemcpyDeviceToDevice, m->stream));
-  CUDA_TRY(cudaMemsetAsync(m->p.counters + kCntActive, 0, sizeof(int), m->stream));
-  CUDA_TRY(cudaMemsetAsync(m->p.counters + kCntKeys, 0, sizeof(int), m->stream));
+  k_frame_begin<<<1, 32, 0, m->stream>>>(m->p.counters);
+  if (int r = check_launch(m)) return r;
   const int threads = 256;
   const int grid_px = pixel_tile_blocks(m->W, m->H, threads);
   if (FieldTraits<V>::is_sdf) {
@@ -231,11 +233,12 @@ RaycastParams make_raycast_params(se_b200_map* m, const float* pose, const float
 }
 
 template <class V>
-int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu) {
+int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu, unsigned long long* stats_dev) {
   const float step = m->dim / (float)m->size;
   const RaycastParams rp = make_raycast_params(m, pose, k, mu, kFarPlane, step * (float)kBlockSide, 1);
   stage_begin(m, SE_B200_STAGE_RAYCAST);
-  k_raycast<V><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal);
+  if (stats_dev) k_raycast<V, true><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
+  else k_raycast<V, false><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RAYCAST);
   return SE_B200_OK;
@@ -331,6 +334,12 @@ extern "C" {
 
 const char* se_b200_last_error(void) { return g_error.c_str(); }
 
+int se_b200_bspline_lut(float out[1000]) {
+  if (!out) return fail(SE_B200_ERR_ARG, "out is null");
+  make_bspline_lut(out);
+  return SE_B200_OK;
+}
+
 int se_b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -382,7 +391,7 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
   if (field_type == SE_B200_OFUSION) {
     CREATE_TRY(cudaMalloc(&m->d_requests, (size_t)m->max_requests * sizeof(unsigned long long)));
     float lut[1000];
-    for (int i = 0; i < 1000; ++i) lut[i] = bspline_closed(-3.f + 6.f * (float)i / 999.f);
+    make_bspline_lut(lut);
     CREATE_TRY(cudaMemcpyToSymbol(c_bspline_lut, lut, sizeof(lut)));
   }
 #undef CREATE_TRY
@@ -488,7 +497,20 @@ int se_b200_raycast(se_b200_map* m, const float pose[16], const float k[4], floa
   REQUIRE_MAP(m);
   if (!pose || !k) return fail(SE_B200_ERR_ARG, "pose/k is null");
   DeviceGuard guard(m->device);
-  return FIELD_DISPATCH(m, raycast_impl<SdfVoxel>(m, pose, k, mu), raycast_impl<OfuVoxel>(m, pose, k, mu));
+  return FIELD_DISPATCH(m, raycast_impl<SdfVoxel>(m, pose, k, mu, nullptr), raycast_impl<OfuVoxel>(m, pose, k, mu, nullptr));
+}
+
+int se_b200_raycast_count_samples(se_b200_map* m, const float pose[16], const float k[4], float mu, uint64_t samples[3]) {
+  REQUIRE_MAP(m);
+  if (!pose || !k || !samples) return fail(SE_B200_ERR_ARG, "null argument");
+  DeviceGuard guard(m->device);
+  Scratch d;
+  CUDA_TRY(d.alloc(3 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(d.p, 0, 3 * sizeof(unsigned long long), m->stream));
+  if (int r = FIELD_DISPATCH(m, raycast_impl<SdfVoxel>(m, pose, k, mu, (unsigned long long*)d.p), raycast_impl<OfuVoxel>(m, pose, k, mu, (unsigned long long*)d.p))) return r;
+  CUDA_TRY(cudaMemcpyAsync(samples, d.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
 }
 
 int se_b200_download_vertex_normal(se_b200_map* m, float* vertex, float* normal) {

@@ -107,7 +107,8 @@ __device__ __forceinline__ int fetch_octant(const MapView<V>& m, int x, int y, i
 // this removes most root-to-leaf descents without changing any result.
 struct BlockCache {
   int bx, by, bz, idx;
-  __device__ __forceinline__ BlockCache() : bx(-1), by(-1), bz(-1), idx(kEmpty) {}
+  int n_get, n_interp, n_grad;     // sample counters (SURVEY 8(d) algorithmic bytes); dead code unless a kernel reads them
+  __device__ __forceinline__ BlockCache() : bx(-1), by(-1), bz(-1), idx(kEmpty), n_get(0), n_interp(0), n_grad(0) {}
 };
 template <class V>
 __device__ __forceinline__ int fetch_block_cached(const MapView<V>& m, BlockCache& c, int x, int y, int z) {
@@ -238,16 +239,19 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, BlockCache& c, V3 
 // metres -> voxels by size/dim; get truncates toward zero, interp/grad floor.
 template <class V>
 __device__ __forceinline__ V vol_get(const MapView<V>& m, BlockCache& c, V3 p) {
+  c.n_get++;
   const float inv = (float)m.size / m.dim;
   return get_fine(m, c, (int)(inv * p.x), (int)(inv * p.y), (int)(inv * p.z));
 }
 template <class V>
 __device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, V3 p) {
+  c.n_interp++;
   const float inv = (float)m.size / m.dim;
   return interp_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
 }
 template <class V>
 __device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, V3 p) {
+  c.n_grad++;
   const float inv = (float)m.size / m.dim;
   return grad_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
 }
