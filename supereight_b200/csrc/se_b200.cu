@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -43,6 +44,7 @@ struct Pools {
   int* block_active = nullptr;
   void* block_data = nullptr;
   int* counters = nullptr;
+  int* dir = nullptr;
 };
 
 }  // namespace
@@ -70,6 +72,7 @@ struct se_b200_map {
   cudaEvent_t ev_begin[SE_B200_NUM_STAGES] = {}, ev_end[SE_B200_NUM_STAGES] = {};
   bool ev_valid[SE_B200_NUM_STAGES] = {};
   long long launches = 0;
+  int grid_integrate = 0;
 
   template <class V> MapView<V> view() const {
     MapView<V> v;
@@ -80,6 +83,7 @@ struct se_b200_map {
     v.block_code = p.block_code; v.block_coord = p.block_coord; v.block_active = p.block_active;
     v.block_data = (V*)p.block_data;
     v.counters = p.counters;
+    v.dir = p.dir; v.dir_dim = size / kBlockSide;
     return v;
   }
 };
@@ -138,6 +142,13 @@ int create_pools(se_b200_map* m) {
   CUDA_TRY(cudaMalloc(&m->p.block_active, nb * sizeof(int)));
   CUDA_TRY(cudaMalloc(&m->p.block_data, nb * kBlockVoxels * sizeof(V)));
   CUDA_TRY(cudaMalloc(&m->p.counters, kNumCounters * sizeof(int)));
+  // block directory: (size/8)^3 ints; skipped above 8192^3 (4 GiB) or when SE_B200_DISABLE_DIRECTORY is set
+  // (the tree descent is then used everywhere; tests run both ways)
+  const size_t g = (size_t)m->size / kBlockSide;
+  if (m->size <= 8192 && !getenv("SE_B200_DISABLE_DIRECTORY")) {
+    CUDA_TRY(cudaMalloc(&m->p.dir, g * g * g * sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(m->p.dir, 0xFF, g * g * g * sizeof(int), m->stream));          // kEmpty
+  }
   CUDA_TRY(cudaMemsetAsync(m->p.node_child, 0xFF, nn * 8 * sizeof(int), m->stream));      // kEmpty
   CUDA_TRY(cudaMemsetAsync(m->p.node_code, 0, nn * sizeof(unsigned long long), m->stream));
   CUDA_TRY(cudaMemsetAsync(m->p.node_side, 0, nn * sizeof(unsigned), m->stream));
@@ -210,12 +221,19 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   ip.voxelSize = voxelsize; ip.mu = mu;
   ip.timestamp = (1.f / 30.f) * (float)frame;                            // DenseSLAMSystem.cpp:243
   ip.W = m->W; ip.H = m->H;
-  const int grid = m->num_sms * 8;          // 8 CTAs x 8 warps per SM: persistent grid-stride loops
-  k_active_list<V><<<grid, threads, 0, m->stream>>>(view, fp, m->d_active_list);
+  // persistent grid-stride kernels: exactly as many CTAs as are resident at once (one wave), trip
+  // counts read from device counters
+  if (m->grid_integrate == 0) {
+    int occ = 0;
+    const void* fn = FieldTraits<V>::is_sdf ? (const void*)k_integrate_sdf : (const void*)k_integrate_ofusion;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0) != cudaSuccess || occ < 1) occ = 2;
+    m->grid_integrate = m->num_sms * occ;
+  }
+  k_active_list<V><<<m->num_sms * 2, threads, 0, m->stream>>>(view, fp, m->d_active_list);
   if (FieldTraits<V>::is_sdf)
-    k_integrate_sdf<<<grid, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
+    k_integrate_sdf<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
   else
-    k_integrate_ofusion<<<grid, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list);
+    k_integrate_ofusion<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list);
   k_update_nodes<V><<<std::max(1, m->num_sms), threads, 0, m->stream>>>(view, m->d_depth, ip);
   if (int r = check_launch(m, 3)) return r;
   stage_end(m, SE_B200_STAGE_FUSE);
@@ -406,7 +424,7 @@ int se_b200_destroy(se_b200_map* m) {
   DeviceGuard guard(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->p.node_child); cudaFree(m->p.node_code); cudaFree(m->p.node_side); cudaFree(m->p.node_mask); cudaFree(m->p.node_value);
-  cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters);
+  cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir);
   cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
   cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_track);
   if (m->h_counters) cudaFreeHost(m->h_counters);

@@ -10,6 +10,8 @@
 //            block_data[512 b + x + 8y + 64z] mirror VoxelBlock<T> (node.hpp:92-145).  One
 //            block's payload is one contiguous, 4 KiB (SDF) / 8 KiB (OFusion) aligned run, so a
 //            warp streams it as float4/int4 rows.
+//   dir    : optional dense (size/8)^3 directory block coordinate -> block index (O(1) fetch);
+//            64^3 x 4 B = 1 MiB at 512^3, 64 MiB at 2048^3 -- affordable with 180 GB of HBM.
 //   counters[kCntNodes/kCntBlocks] are bump allocators (MemoryPool::acquire_block,
 //            se_core/include/se/utils/memory_pool.hpp:69-76); pools are pre-initialised to
 //            initValue() at creation, so allocation never touches the payload.
@@ -60,6 +62,12 @@ template <class V> struct MapView {
   int* block_active;
   V* block_data;
   int* counters;
+  // Block directory: dense (size/8)^3 grid of block indices (kEmpty where nothing is allocated),
+  // cell = bx + G (by + G bz).  It turns Octree::fetch into one load.  The octree nodes stay the
+  // authoritative structure (ray walk, node values, export); the directory is a pure index on the
+  // leaves, written once when a block is created.  nullptr => fall back to the tree descent.
+  int* dir;
+  int dir_dim;         // G = size / 8
 };
 
 // ---- device accessors -------------------------------------------------------------------
@@ -77,6 +85,7 @@ __device__ __forceinline__ bool in_volume(const MapView<V>& m, int x, int y, int
 template <class V>
 __device__ __forceinline__ int fetch_block(const MapView<V>& m, int x, int y, int z) {
   if (!in_volume(m, x, y, z)) return kEmpty;
+  if (m.dir) return __ldg(m.dir + ((z >> 3) * m.dir_dim + (y >> 3)) * m.dir_dim + (x >> 3));
   int n = 0;
   for (int edge = m.size >> 1; edge >= kBlockSide; edge >>= 1) {
     const int slot = ((x & edge) != 0) | (((y & edge) != 0) << 1) | (((z & edge) != 0) << 2);
@@ -206,7 +215,42 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, BlockCache& c, V3 
   const int x_ll = max(b0 - 1, 0), x_lu = max(b0, 0), x_ul = min(b0 + 1, hi), x_uu = min(b0 + 2, hi);
   const int y_ll = max(b1 - 1, 0), y_lu = max(b1, 0), y_ul = min(b1 + 1, hi), y_uu = min(b1 + 2, hi);
   const int z_ll = max(b2 - 1, 0), z_lu = max(b2, 0), z_ul = min(b2 + 1, hi), z_uu = min(b2 + 2, hi);
-  // the 32 distinct samples: 4 x-values at the 4 (y,z) of the inner square, etc.
+  // Fast path (the 4x4x4 neighbourhood b-1..b+2 lies inside one block, so no clamp is active): one
+  // fetch, then the 32 distinct samples at constant offsets from the base voxel (the compiler merges
+  // the 48 reads of the expression below into 32 loads).  Same values, same arithmetic as the
+  // general path.
+  if (((b0 & 7) >= 1) & ((b0 & 7) <= 5) & ((b1 & 7) >= 1) & ((b1 & 7) <= 5) & ((b2 & 7) >= 1) & ((b2 & 7) <= 5) & in_volume(m, b0, b1, b2)) {
+    const int blk = fetch_block_cached(m, c, b0, b1, b2);
+    if (blk < 0) return v3(0.f, 0.f, 0.f);          // every sample is initValue(): all differences are +0
+    const V* q = m.block_data + (size_t)blk * kBlockVoxels + voxel_offset<V>(b0, b1, b2);
+#define S(X, Y, Z) load_x(q + (X) + 8 * (Y) + 64 * (Z))
+    V3 r;
+    {
+      const float t00 = (S(1, 0, 0) - S(-1, 0, 0)) * wx0 + (S(2, 0, 0) - S(0, 0, 0)) * wx1;
+      const float t10 = (S(1, 1, 0) - S(-1, 1, 0)) * wx0 + (S(2, 1, 0) - S(0, 1, 0)) * wx1;
+      const float t01 = (S(1, 0, 1) - S(-1, 0, 1)) * wx0 + (S(2, 0, 1) - S(0, 0, 1)) * wx1;
+      const float t11 = (S(1, 1, 1) - S(-1, 1, 1)) * wx0 + (S(2, 1, 1) - S(0, 1, 1)) * wx1;
+      r.x = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
+    }
+    {
+      const float t00 = (S(0, 1, 0) - S(0, -1, 0)) * wx0 + (S(1, 1, 0) - S(1, -1, 0)) * wx1;
+      const float t10 = (S(0, 2, 0) - S(0, 0, 0)) * wx0 + (S(1, 2, 0) - S(1, 0, 0)) * wx1;
+      const float t01 = (S(0, 1, 1) - S(0, -1, 1)) * wx0 + (S(1, 1, 1) - S(1, -1, 1)) * wx1;
+      const float t11 = (S(0, 2, 1) - S(0, 0, 1)) * wx0 + (S(1, 2, 1) - S(1, 0, 1)) * wx1;
+      r.y = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
+    }
+    {
+      const float t00 = (S(0, 0, 1) - S(0, 0, -1)) * wx0 + (S(1, 0, 1) - S(1, 0, -1)) * wx1;
+      const float t10 = (S(0, 1, 1) - S(0, 1, -1)) * wx0 + (S(1, 1, 1) - S(1, 1, -1)) * wx1;
+      const float t01 = (S(0, 0, 2) - S(0, 0, 0)) * wx0 + (S(1, 0, 2) - S(1, 0, 0)) * wx1;
+      const float t11 = (S(0, 1, 2) - S(0, 1, 0)) * wx0 + (S(1, 1, 2) - S(1, 1, 0)) * wx1;
+      r.z = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
+    }
+#undef S
+    const float s = (0.5f * m.dim) / (float)m.size;
+    return v3(s * r.x, s * r.y, s * r.z);
+  }
+  // general path: the 32 distinct samples, each through the cached block lookup
 #define G(X, Y, Z) get_fine_x(m, c, (X), (Y), (Z))
   V3 r;
   {
@@ -262,7 +306,9 @@ __device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, V3 p)
 // A missing child slot is claimed with atomicCAS(kEmpty -> kBusy); the winner takes an index
 // from the bump allocator, fills the metadata, and publishes the index with a fence; losers
 // re-read the slot until it is published.  The winner never waits on anyone, so the scheme is
-// starvation-free under independent thread scheduling.
+// starvation-free under independent thread scheduling.  A new block is also entered in the
+// directory (after it is published in the tree; a reader that still sees kEmpty there falls back
+// to this walk, which finds the block).
 // Returns the node/block index, or kEmpty when a pool is exhausted (error bit set);
 // created_target tells whether this call created the octant at target_level itself.
 template <class V>
@@ -273,7 +319,10 @@ __device__ __forceinline__ int find_or_create(const MapView<V>& m, unsigned long
   for (int level = 1; level <= target_level; ++level, edge >>= 1) {
     const int slot = key_child_id(code, level, m.max_level);
     int* p = m.node_child + 8 * n + slot;
-    int c = __ldcg(p);
+    // First read through L1: published indices never change, and a stale kEmpty/kBusy is re-validated
+    // by the atomicCAS / volatile re-read below.  (Reading the hot upper levels through L2 only made
+    // every walk of every warp queue on the same few L2 lines.)
+    int c = __ldca(p);
     while (c < 0) {
       if (c == kEmpty) {
         const int old = atomicCAS(p, kEmpty, kBusy);
@@ -308,6 +357,11 @@ __device__ __forceinline__ int find_or_create(const MapView<V>& m, unsigned long
           atomicOr(m.node_mask + n, 1u << slot);
           __threadfence();
           atomicExch(p, idx);
+          if (level == m.leaves_level && m.dir) {
+            int x, y, z;
+            morton_decode(prefix, x, y, z);
+            atomicExch(m.dir + ((z >> 3) * m.dir_dim + (y >> 3)) * m.dir_dim + (x >> 3), idx);
+          }
           c = idx;
         } else {
           c = old;
