@@ -255,8 +255,8 @@ int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu, un
   const float step = m->dim / (float)m->size;
   const RaycastParams rp = make_raycast_params(m, pose, k, mu, kFarPlane, step * (float)kBlockSide, 1);
   stage_begin(m, SE_B200_STAGE_RAYCAST);
-  if (stats_dev) k_raycast<V, true><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
-  else k_raycast<V, false><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
+  if (stats_dev) k_raycast<V, true><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
+  else k_raycast<V, false><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RAYCAST);
   return SE_B200_OK;
@@ -267,7 +267,7 @@ int render_volume_impl(se_b200_map* m, uchar4* out_dev, const float* view_pose, 
   const RaycastParams rp = make_raycast_params(m, view_pose, k, mu, kFarPlane * 2.0f, largestep, 0);   // DenseSLAMSystem.cpp:283-288
   const V3 light = v3(view_pose[3], view_pose[7], view_pose[11]);
   stage_begin(m, SE_B200_STAGE_RENDER);
-  k_render_volume<V><<<pixel_tile_blocks(m->W, m->H, 128), 128, 0, m->stream>>>(m->view<V>(), rp, light, reraycast, m->d_vertex, m->d_normal, out_dev);
+  k_render_volume<V><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, light, reraycast, m->d_vertex, m->d_normal, out_dev);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RENDER);
   return SE_B200_OK;
@@ -694,8 +694,8 @@ int se_b200_query_grad(se_b200_map* m, const float* pos, int n, float* out) {
   CUDA_TRY(dx.alloc((size_t)n * 3 * sizeof(float)));
   CUDA_TRY(dout.alloc((size_t)n * 3 * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(dx.p, pos, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-  if (m->field == SE_B200_SDF) k_query_grad<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, (float*)dout.p);
-  else k_query_grad<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  if (m->field == SE_B200_SDF) k_query_grad<SdfVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  else k_query_grad<OfuVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, (float*)dout.p);
   if (int r = check_launch(m)) return r;
   CUDA_TRY(cudaMemcpyAsync(out, dout.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -728,8 +728,8 @@ int se_b200_query_rays(se_b200_map* m, const float* origin_dir, int n, float nea
   CUDA_TRY(dk.alloc((size_t)n * sizeof(unsigned long long)));
   CUDA_TRY(dt.alloc((size_t)n * 3 * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(dx.p, origin_dir, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-  if (m->field == SE_B200_SDF) k_query_ray<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
-  else k_query_ray<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+  if (m->field == SE_B200_SDF) k_query_ray<SdfVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+  else k_query_ray<OfuVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
   if (int r = check_launch(m)) return r;
   if (first_block_key) CUDA_TRY(cudaMemcpyAsync(first_block_key, dk.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
   if (tinfo) CUDA_TRY(cudaMemcpyAsync(tinfo, dt.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));

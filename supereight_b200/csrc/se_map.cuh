@@ -82,10 +82,9 @@ __device__ __forceinline__ bool in_volume(const MapView<V>& m, int x, int y, int
 // outside the volume read as "not allocated" (the reference indexes out of bounds there).
 // Read-only accessors (this one, get_fine, interp, grad) go through the non-coherent cache
 // (__ldg): they are only used by kernels that do not modify the tree.
+// the tree descent itself, kept out of line: with the directory it is only the fallback
 template <class V>
-__device__ __forceinline__ int fetch_block(const MapView<V>& m, int x, int y, int z) {
-  if (!in_volume(m, x, y, z)) return kEmpty;
-  if (m.dir) return __ldg(m.dir + ((z >> 3) * m.dir_dim + (y >> 3)) * m.dir_dim + (x >> 3));
+__device__ __noinline__ int fetch_block_tree(const MapView<V>& m, int x, int y, int z) {
   int n = 0;
   for (int edge = m.size >> 1; edge >= kBlockSide; edge >>= 1) {
     const int slot = ((x & edge) != 0) | (((y & edge) != 0) << 1) | (((z & edge) != 0) << 2);
@@ -93,6 +92,12 @@ __device__ __forceinline__ int fetch_block(const MapView<V>& m, int x, int y, in
     if (n < 0) return kEmpty;
   }
   return n;
+}
+template <class V>
+__device__ __forceinline__ int fetch_block(const MapView<V>& m, int x, int y, int z) {
+  if (!in_volume(m, x, y, z)) return kEmpty;
+  if (m.dir) return __ldg(m.dir + ((z >> 3) * m.dir_dim + (y >> 3)) * m.dir_dim + (x >> 3));
+  return fetch_block_tree(m, x, y, z);
 }
 
 // Octree::fetch_octant (octree.hpp:460-478): node/block at `depth`, is_block tells which pool.
@@ -203,78 +208,91 @@ __device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c
          + (p[6] * (1 - fx) + p[7] * fx) * fy) * fz);
 }
 
-// Octree::grad(pos, select) (octree.hpp:652-737): central differences blended trilinearly
+// Octree::grad(pos, select) (octree.hpp:652-737): central differences blended trilinearly.
+// The 48 reads of the reference expression touch 32 distinct voxels: per axis the clamped
+// coordinates {ll, lu, ul, uu} = {max(b-1,0), max(b,0), min(b+1,hi), min(b+2,hi)}, which span at most
+// two blocks per axis.  The (at most) 8 block indices are looked up once into `ids` (a per-thread
+// column of shared memory); every sample then is: pick the block by three 0/1 selectors, one load.
+// Same values and the same float expression as the reference -- only the addressing differs.
 template <class V>
-__device__ __forceinline__ V3 grad_field(const MapView<V>& m, BlockCache& c, V3 pos) {
+__device__ __forceinline__ V3 grad_field(const MapView<V>& m, int (*ids)[/*threads*/ 128], V3 pos) {
   const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
   const int b0 = (int)flx, b1 = (int)fly, b2 = (int)flz;
   const float wx1 = pos.x - flx, wy1 = pos.y - fly, wz1 = pos.z - flz;
   const float wx0 = 1 - wx1, wy0 = 1 - wy1, wz0 = 1 - wz1;
   const int hi = m.size - 1;
-  // per axis: ll = max(b-1,0), lu = max(b,0), ul = min(b+1,hi), uu = min(b+2,hi)
-  const int x_ll = max(b0 - 1, 0), x_lu = max(b0, 0), x_ul = min(b0 + 1, hi), x_uu = min(b0 + 2, hi);
-  const int y_ll = max(b1 - 1, 0), y_lu = max(b1, 0), y_ul = min(b1 + 1, hi), y_uu = min(b1 + 2, hi);
-  const int z_ll = max(b2 - 1, 0), z_lu = max(b2, 0), z_ul = min(b2 + 1, hi), z_uu = min(b2 + 2, hi);
-  // Fast path (the 4x4x4 neighbourhood b-1..b+2 lies inside one block, so no clamp is active): one
-  // fetch, then the 32 distinct samples at constant offsets from the base voxel (the compiler merges
-  // the 48 reads of the expression below into 32 loads).  Same values, same arithmetic as the
-  // general path.
-  if (((b0 & 7) >= 1) & ((b0 & 7) <= 5) & ((b1 & 7) >= 1) & ((b1 & 7) <= 5) & ((b2 & 7) >= 1) & ((b2 & 7) <= 5) & in_volume(m, b0, b1, b2)) {
-    const int blk = fetch_block_cached(m, c, b0, b1, b2);
-    if (blk < 0) return v3(0.f, 0.f, 0.f);          // every sample is initValue(): all differences are +0
-    const V* q = m.block_data + (size_t)blk * kBlockVoxels + voxel_offset<V>(b0, b1, b2);
-#define S(X, Y, Z) load_x(q + (X) + 8 * (Y) + 64 * (Z))
-    V3 r;
-    {
-      const float t00 = (S(1, 0, 0) - S(-1, 0, 0)) * wx0 + (S(2, 0, 0) - S(0, 0, 0)) * wx1;
-      const float t10 = (S(1, 1, 0) - S(-1, 1, 0)) * wx0 + (S(2, 1, 0) - S(0, 1, 0)) * wx1;
-      const float t01 = (S(1, 0, 1) - S(-1, 0, 1)) * wx0 + (S(2, 0, 1) - S(0, 0, 1)) * wx1;
-      const float t11 = (S(1, 1, 1) - S(-1, 1, 1)) * wx0 + (S(2, 1, 1) - S(0, 1, 1)) * wx1;
-      r.x = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
-    }
-    {
-      const float t00 = (S(0, 1, 0) - S(0, -1, 0)) * wx0 + (S(1, 1, 0) - S(1, -1, 0)) * wx1;
-      const float t10 = (S(0, 2, 0) - S(0, 0, 0)) * wx0 + (S(1, 2, 0) - S(1, 0, 0)) * wx1;
-      const float t01 = (S(0, 1, 1) - S(0, -1, 1)) * wx0 + (S(1, 1, 1) - S(1, -1, 1)) * wx1;
-      const float t11 = (S(0, 2, 1) - S(0, 0, 1)) * wx0 + (S(1, 2, 1) - S(1, 0, 1)) * wx1;
-      r.y = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
-    }
-    {
-      const float t00 = (S(0, 0, 1) - S(0, 0, -1)) * wx0 + (S(1, 0, 1) - S(1, 0, -1)) * wx1;
-      const float t10 = (S(0, 1, 1) - S(0, 1, -1)) * wx0 + (S(1, 1, 1) - S(1, 1, -1)) * wx1;
-      const float t01 = (S(0, 0, 2) - S(0, 0, 0)) * wx0 + (S(1, 0, 2) - S(1, 0, 0)) * wx1;
-      const float t11 = (S(0, 1, 2) - S(0, 1, 0)) * wx0 + (S(1, 1, 2) - S(1, 1, 0)) * wx1;
-      r.z = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
-    }
-#undef S
-    const float s = (0.5f * m.dim) / (float)m.size;
-    return v3(s * r.x, s * r.y, s * r.z);
+  // Packed per axis-coordinate code: (block selector 0/1) << 16|17|18, offset inside the block
+  // pre-scaled in the low 9 bits, bit 28+ set when the coordinate lies outside [0, hi].  (The
+  // reference clamps only one side of each coordinate -- max(b,0) can exceed hi, min(b+1,hi) can be
+  // negative when the position is outside the volume -- and then reads out of bounds; here such a
+  // sample reads initValue(), like get_fine on an unallocated block.)
+  int cx[4], cy[4], cz[4];
+  const int x4[4] = { max(b0 - 1, 0), max(b0, 0), min(b0 + 1, hi), min(b0 + 2, hi) };
+  const int y4[4] = { max(b1 - 1, 0), max(b1, 0), min(b1 + 1, hi), min(b1 + 2, hi) };
+  const int z4[4] = { max(b2 - 1, 0), max(b2, 0), min(b2 + 1, hi), min(b2 + 2, hi) };
+  int Bx = 0x7fffffff, By = 0x7fffffff, Bz = 0x7fffffff;      // lowest block touched per axis
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if ((unsigned)x4[j] <= (unsigned)hi) Bx = min(Bx, x4[j] >> 3);
+    if ((unsigned)y4[j] <= (unsigned)hi) By = min(By, y4[j] >> 3);
+    if ((unsigned)z4[j] <= (unsigned)hi) Bz = min(Bz, z4[j] >> 3);
   }
-  // general path: the 32 distinct samples, each through the cached block lookup
-#define G(X, Y, Z) get_fine_x(m, c, (X), (Y), (Z))
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    cx[j] = (unsigned)x4[j] <= (unsigned)hi ? ((((x4[j] >> 3) - Bx) << 16) | (x4[j] & 7)) : (1 << 28);
+    cy[j] = (unsigned)y4[j] <= (unsigned)hi ? ((((y4[j] >> 3) - By) << 17) | ((y4[j] & 7) << 3)) : (1 << 28);
+    cz[j] = (unsigned)z4[j] <= (unsigned)hi ? ((((z4[j] >> 3) - Bz) << 18) | ((z4[j] & 7) << 6)) : (1 << 28);
+  }
+  const int t = threadIdx.x;
+  const int G = m.size >> 3;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int gx = Bx + (s & 1), gy = By + ((s >> 1) & 1), gz = Bz + (s >> 2);
+    int id = kEmpty;
+    if (((unsigned)gx < (unsigned)G) & ((unsigned)gy < (unsigned)G) & ((unsigned)gz < (unsigned)G)) id = fetch_block(m, gx << 3, gy << 3, gz << 3);
+    ids[s][t] = id;
+  }
+  const float initx = FieldTraits<V>::init().x;
+#define S(JX, JY, JZ) ([&]() { const int code = cx[JX] + cy[JY] + cz[JZ]; const int id = ids[(code >> 16) & 7][t]; \
+                               return ((code >> 28) != 0 || id < 0) ? initx : load_x(m.block_data + (size_t)id * kBlockVoxels + (code & 0x1ff)); }())
+  // the 32 distinct samples (indices into {ll, lu, ul, uu} per axis: 0..3; lower = 1, upper = 2)
+  const float x_a00 = S(0, 1, 1), x_b00 = S(1, 1, 1), x_c00 = S(2, 1, 1), x_d00 = S(3, 1, 1);
+  const float x_a10 = S(0, 2, 1), x_b10 = S(1, 2, 1), x_c10 = S(2, 2, 1), x_d10 = S(3, 2, 1);
+  const float x_a01 = S(0, 1, 2), x_b01 = S(1, 1, 2), x_c01 = S(2, 1, 2), x_d01 = S(3, 1, 2);
+  const float x_a11 = S(0, 2, 2), x_b11 = S(1, 2, 2), x_c11 = S(2, 2, 2), x_d11 = S(3, 2, 2);
+  const float y_a00 = S(1, 0, 1), y_d00 = S(1, 3, 1), y_a10 = S(2, 0, 1), y_d10 = S(2, 3, 1);
+  const float y_a01 = S(1, 0, 2), y_d01 = S(1, 3, 2), y_a11 = S(2, 0, 2), y_d11 = S(2, 3, 2);
+  const float z_a00 = S(1, 1, 0), z_d00 = S(1, 1, 3), z_a10 = S(2, 1, 0), z_d10 = S(2, 1, 3);
+  const float z_a01 = S(1, 2, 0), z_d01 = S(1, 2, 3), z_a11 = S(2, 2, 0), z_d11 = S(2, 2, 3);
+#undef S
+  // inner 2x2x2 (x index 1|2, y 1|2, z 1|2) by name: x_b/x_c rows above
+  // v(x,y,z) with x,y,z in {1,2}:  v(1,1,1)=x_b00 v(2,1,1)=x_c00 v(1,2,1)=x_b10 v(2,2,1)=x_c10
+  //                                v(1,1,2)=x_b01 v(2,1,2)=x_c01 v(1,2,2)=x_b11 v(2,2,2)=x_c11
   V3 r;
   {
-    const float t00 = (G(x_ul, y_lu, z_lu) - G(x_ll, y_lu, z_lu)) * wx0 + (G(x_uu, y_lu, z_lu) - G(x_lu, y_lu, z_lu)) * wx1;
-    const float t10 = (G(x_ul, y_ul, z_lu) - G(x_ll, y_ul, z_lu)) * wx0 + (G(x_uu, y_ul, z_lu) - G(x_lu, y_ul, z_lu)) * wx1;
-    const float t01 = (G(x_ul, y_lu, z_ul) - G(x_ll, y_lu, z_ul)) * wx0 + (G(x_uu, y_lu, z_ul) - G(x_lu, y_lu, z_ul)) * wx1;
-    const float t11 = (G(x_ul, y_ul, z_ul) - G(x_ll, y_ul, z_ul)) * wx0 + (G(x_uu, y_ul, z_ul) - G(x_lu, y_ul, z_ul)) * wx1;
+    // gradient(0): octree.hpp:669-689
+    const float t00 = (x_c00 - x_a00) * wx0 + (x_d00 - x_b00) * wx1;
+    const float t10 = (x_c10 - x_a10) * wx0 + (x_d10 - x_b10) * wx1;
+    const float t01 = (x_c01 - x_a01) * wx0 + (x_d01 - x_b01) * wx1;
+    const float t11 = (x_c11 - x_a11) * wx0 + (x_d11 - x_b11) * wx1;
     r.x = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
   }
   {
-    const float t00 = (G(x_lu, y_ul, z_lu) - G(x_lu, y_ll, z_lu)) * wx0 + (G(x_ul, y_ul, z_lu) - G(x_ul, y_ll, z_lu)) * wx1;
-    const float t10 = (G(x_lu, y_uu, z_lu) - G(x_lu, y_lu, z_lu)) * wx0 + (G(x_ul, y_uu, z_lu) - G(x_ul, y_lu, z_lu)) * wx1;
-    const float t01 = (G(x_lu, y_ul, z_ul) - G(x_lu, y_ll, z_ul)) * wx0 + (G(x_ul, y_ul, z_ul) - G(x_ul, y_ll, z_ul)) * wx1;
-    const float t11 = (G(x_lu, y_uu, z_ul) - G(x_lu, y_lu, z_ul)) * wx0 + (G(x_ul, y_uu, z_ul) - G(x_ul, y_lu, z_ul)) * wx1;
+    // gradient(1): octree.hpp:691-711 ; y index 0..3 at x in {1,2}
+    const float t00 = (x_b10 - y_a00) * wx0 + (x_c10 - y_a10) * wx1;     // (v(lo,ul,lo) - v(lo,ll,lo)), (v(up,ul,lo) - v(up,ll,lo))
+    const float t10 = (y_d00 - x_b00) * wx0 + (y_d10 - x_c00) * wx1;     // (v(lo,uu,lo) - v(lo,lu,lo)), (v(up,uu,lo) - v(up,lu,lo))
+    const float t01 = (x_b11 - y_a01) * wx0 + (x_c11 - y_a11) * wx1;
+    const float t11 = (y_d01 - x_b01) * wx0 + (y_d11 - x_c01) * wx1;
     r.y = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
   }
   {
-    const float t00 = (G(x_lu, y_lu, z_ul) - G(x_lu, y_lu, z_ll)) * wx0 + (G(x_ul, y_lu, z_ul) - G(x_ul, y_lu, z_ll)) * wx1;
-    const float t10 = (G(x_lu, y_ul, z_ul) - G(x_lu, y_ul, z_ll)) * wx0 + (G(x_ul, y_ul, z_ul) - G(x_ul, y_ul, z_ll)) * wx1;
-    const float t01 = (G(x_lu, y_lu, z_uu) - G(x_lu, y_lu, z_lu)) * wx0 + (G(x_ul, y_lu, z_uu) - G(x_ul, y_lu, z_lu)) * wx1;
-    const float t11 = (G(x_lu, y_ul, z_uu) - G(x_lu, y_ul, z_lu)) * wx0 + (G(x_ul, y_ul, z_uu) - G(x_ul, y_ul, z_lu)) * wx1;
+    // gradient(2): octree.hpp:713-733 ; z index 0..3 at (x,y) in {1,2}^2
+    const float t00 = (x_b01 - z_a00) * wx0 + (x_c01 - z_a10) * wx1;     // y = lo: (v(lo,lo,ul) - v(lo,lo,ll)), (v(up,lo,ul) - v(up,lo,ll))
+    const float t10 = (x_b11 - z_a01) * wx0 + (x_c11 - z_a11) * wx1;     // y = up
+    const float t01 = (z_d00 - x_b00) * wx0 + (z_d10 - x_c00) * wx1;     // y = lo: (v(lo,lo,uu) - v(lo,lo,lu)), ...
+    const float t11 = (z_d01 - x_b10) * wx0 + (z_d11 - x_c10) * wx1;     // y = up
     r.z = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
   }
-#undef G
   const float s = (0.5f * m.dim) / (float)m.size;
   return v3(s * r.x, s * r.y, s * r.z);
 }
@@ -294,10 +312,10 @@ __device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, 
   return interp_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
 }
 template <class V>
-__device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, V3 p) {
+__device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 p) {
   c.n_grad++;
   const float inv = (float)m.size / m.dim;
-  return grad_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
+  return grad_field(m, ids, v3(inv * p.x, inv * p.y, inv * p.z));
 }
 
 // ---- insertion -----------------------------------------------------------------------------

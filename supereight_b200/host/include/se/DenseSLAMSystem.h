@@ -1,0 +1,129 @@
+// DenseSLAMSystem.h -- the reference's pipeline class
+// (se_denseslam/include/se/DenseSLAMSystem.h:58-411) with the same public methods, argument
+// meaning and return conventions, implemented on top of the C ABI of include/se_b200.h: the map,
+// the images and every kernel live on the GPU.
+//
+// As in the reference the field type is a compile-time choice: build with
+// -DSE_FIELD_TYPE=SDF or -DSE_FIELD_TYPE=OFusion (se_denseslam/CMakeLists.txt:31-50).
+//
+// What differs from the reference, by design:
+//  * getMap() cannot hand out a host se::Octree (the map is in HBM): it returns a snapshot
+//    (se::MapSnapshot: blocks and nodes sorted by key, the comparable form of Octree::save,
+//    se_core/include/se/octree.hpp:897-915).
+//  * tracking() (ICP) is not on the GPU path yet: it returns false and leaves the
+//    pose untouched; supply poses with setPose() (the reference's ground-truth mode,
+//    se_apps/src/mainQt.cpp:257-265).
+//  * errors the reference handles with exit(1) (bad size ratio, preprocessing.cpp:165-176)
+//    do the same here, with the library's message.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "config.h"
+#include "eigen_lite.h"
+
+struct se_b200_map;
+
+#ifndef SE_FIELD_TYPE
+#define SE_FIELD_TYPE SDF
+#endif
+struct SDF { float x; float y; };                      // volume_traits.hpp:41-44
+struct OFusion { float x; double y; };                 // volume_traits.hpp:62-65
+typedef SE_FIELD_TYPE FieldType;
+
+namespace se {
+struct MapSnapshot {                                   // what Octree::save writes, sorted by key
+  int size = 0;
+  float dim = 0.f;
+  std::vector<uint64_t> block_keys;
+  std::vector<int32_t> block_coords;                   // 3 per block
+  std::vector<FieldType> block_voxels;                 // 512 per block, x + 8 y + 64 z
+  std::vector<uint64_t> node_codes;
+  std::vector<uint32_t> node_sides;
+  std::vector<FieldType> node_values;                  // 8 per node
+};
+}  // namespace se
+
+class DenseSLAMSystem {
+ public:
+  EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+  // DenseSLAMSystem.h:111-134.  Only .x() of the resolution / dimensions is used (cubic volume,
+  // DenseSLAMSystem.cpp:123-125).
+  DenseSLAMSystem(const Eigen::Vector2i& inputSize, const Eigen::Vector3i& volumeResolution,
+                  const Eigen::Vector3f& volumeDimensions, const Eigen::Vector3f& initPose,
+                  std::vector<int>& pyramid, const Configuration& config);
+  DenseSLAMSystem(const Eigen::Vector2i& inputSize, const Eigen::Vector3i& volumeResolution,
+                  const Eigen::Vector3f& volumeDimensions, const Eigen::Matrix4f& initPose,
+                  std::vector<int>& pyramid, const Configuration& config);
+  ~DenseSLAMSystem();
+  DenseSLAMSystem(const DenseSLAMSystem&) = delete;
+  DenseSLAMSystem& operator=(const DenseSLAMSystem&) = delete;
+
+  // :147  mm -> m (+ sub-sampling to the computation size); `filterInput` only feeds tracking (N1)
+  bool preprocessing(const unsigned short* inputDepth, const Eigen::Vector2i& inputSize, bool filterInput);
+  // :173  see the header comment
+  bool tracking(const Eigen::Vector4f& k, float icp_threshold, unsigned tracking_rate, unsigned frame);
+  // :193  runs when frame % integration_rate == 0 or frame <= 3 (DenseSLAMSystem.cpp:209)
+  bool integration(const Eigen::Vector4f& k, unsigned integration_rate, float mu, unsigned frame);
+  // :212  runs when frame > 2 (DenseSLAMSystem.cpp:195); latches raycast_pose_
+  bool raycasting(const Eigen::Vector4f& k, float mu, unsigned frame);
+  // :219-224
+  void dump_volume(const std::string filename);
+  void dump_mesh(const std::string filename);
+  // :241  out = W*H*4 bytes RGBA, caller-owned; runs when frame % rate == 0 (DenseSLAMSystem.cpp:281)
+  void renderVolume(unsigned char* out, const Eigen::Vector2i& outputSize, int frame, int rate,
+                    const Eigen::Vector4f& k, float mu);
+  void renderTrack(unsigned char* out, const Eigen::Vector2i& outputSize);   // :268
+  void renderDepth(unsigned char* out, const Eigen::Vector2i& outputSize);   // :285
+
+  void getMap(std::shared_ptr<se::MapSnapshot>& out);                         // :295 (see header comment)
+  bool getTracked() { return tracked_; }
+  bool getIntegrated() { return integrated_; }
+  Eigen::Vector3f getPosition() {                                             // :318-325
+    return Eigen::Vector3f(pose_(0, 3) - init_pose_.x(), pose_(1, 3) - init_pose_.y(), pose_(2, 3) - init_pose_.z());
+  }
+  Eigen::Vector3f getInitPos() { return init_pose_; }
+  Eigen::Matrix4f getPose() { return pose_; }
+  void setPose(const Eigen::Matrix4f pose) {                                  // :353-356: adds init_pose_
+    pose_ = pose;
+    pose_(0, 3) += init_pose_.x(); pose_(1, 3) += init_pose_.y(); pose_(2, 3) += init_pose_.z();
+  }
+  void setViewPose(Eigen::Matrix4f* value = nullptr) {                        // :363-372: keeps the caller's pointer
+    if (value == nullptr) { viewPose_ = &pose_; need_render_ = false; }
+    else { viewPose_ = value; need_render_ = true; }
+  }
+  Eigen::Matrix4f* getViewPose() { return viewPose_; }
+  Eigen::Vector3f getModelDimensions() { return volume_dimension_; }
+  Eigen::Vector3i getModelResolution() { return volume_resolution_; }
+  Eigen::Vector2i getComputationResolution() { return computation_size_; }
+
+  // -- additions (not in the reference) ----------------------------------------------------------
+  // vertex / normal maps of the last raycast (W*H*3 floats each), for callers that consume them
+  void getVertexNormal(std::vector<float>& vertex, std::vector<float>& normal);
+  // device time of the last run of a stage in ms (stands in for the TICK/TOCK samples, se_shared/timings.h)
+  float stageMilliseconds(int stage);
+  se_b200_map* handle() { return map_; }
+
+ private:
+  Eigen::Vector2i computation_size_;
+  Eigen::Matrix4f pose_;
+  Eigen::Matrix4f* viewPose_;
+  Eigen::Vector3f volume_dimension_;
+  Eigen::Vector3i volume_resolution_;
+  std::vector<int> iterations_;
+  bool tracked_ = false;
+  bool integrated_ = false;
+  Eigen::Vector3f init_pose_;
+  float mu_;
+  bool need_render_ = false;
+  Configuration config_;
+  Eigen::Matrix4f raycast_pose_;
+  std::vector<int> tracking_result_;          // TrackData (8 ints per pixel, commons.h:249-253)
+  se_b200_map* map_ = nullptr;
+};
+
+// DenseSLAMSystem.h:418: declared by the reference, never defined there; here it really synchronises
+void synchroniseDevices();

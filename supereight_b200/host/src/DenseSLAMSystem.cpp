@@ -1,0 +1,155 @@
+// DenseSLAMSystem.cpp -- the reference's pipeline object (se_denseslam/src/DenseSLAMSystem.cpp)
+// as a thin host-side shim: stage gating, pose state and argument checks here, all computation
+// behind the C ABI (include/se_b200.h) on the GPU.  No CPU fallback: if the library reports an
+// error the process stops with its message, like the reference's exit(1) paths.
+#include "se/DenseSLAMSystem.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+#include "se_b200.h"
+
+namespace {
+constexpr int kFieldType = std::is_same<FieldType, SDF>::value ? SE_B200_SDF : SE_B200_OFUSION;
+static_assert(sizeof(SDF) == sizeof(se_b200_sdf_voxel) && sizeof(OFusion) == sizeof(se_b200_ofusion_voxel), "voxel layout");
+
+void pack(const Eigen::Matrix4f& m, float out[16]) {
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[4 * r + c] = m(r, c);
+}
+void pack(const Eigen::Vector4f& k, float out[4]) { for (int i = 0; i < 4; ++i) out[i] = k(i); }
+[[noreturn]] void die(const char* where) {
+  std::fprintf(stderr, "%s: %s\n", where, se_b200_last_error());
+  std::exit(1);
+}
+#define SE_CHECK(call, where) do { if ((call) != SE_B200_OK) die(where); } while (0)
+
+Eigen::Matrix4f translation(const Eigen::Vector3f& t) {      // se::math::toMatrix4f (math_utils.h:90-97)
+  Eigen::Matrix4f m = Eigen::Matrix4f::Identity();
+  m(0, 3) = t.x(); m(1, 3) = t.y(); m(2, 3) = t.z();
+  return m;
+}
+se_b200_map* g_last_map = nullptr;
+}  // namespace
+
+DenseSLAMSystem::DenseSLAMSystem(const Eigen::Vector2i& inputSize, const Eigen::Vector3i& volumeResolution,
+                                 const Eigen::Vector3f& volumeDimensions, const Eigen::Vector3f& initPose,
+                                 std::vector<int>& pyramid, const Configuration& config)
+    : DenseSLAMSystem(inputSize, volumeResolution, volumeDimensions, translation(initPose), pyramid, config) {}
+
+DenseSLAMSystem::DenseSLAMSystem(const Eigen::Vector2i& inputSize, const Eigen::Vector3i& volumeResolution,
+                                 const Eigen::Vector3f& volumeDimensions, const Eigen::Matrix4f& initPose,
+                                 std::vector<int>& pyramid, const Configuration& config)
+    : computation_size_(inputSize), config_(config) {
+  init_pose_ = Eigen::Vector3f(initPose(0, 3), initPose(1, 3), initPose(2, 3));      // DenseSLAMSystem.cpp:77
+  volume_dimension_ = volumeDimensions;
+  volume_resolution_ = volumeResolution;
+  mu_ = config.mu;
+  pose_ = initPose;
+  raycast_pose_ = initPose;
+  iterations_ = pyramid;
+  viewPose_ = &pose_;
+  tracking_result_.assign((size_t)inputSize.x() * inputSize.y() * 8, 0);
+  const char* dev = std::getenv("SE_B200_DEVICE");
+  SE_CHECK(se_b200_create(&map_, kFieldType, volumeResolution.x(), volumeDimensions.x(), inputSize.x(), inputSize.y(),
+                          0, 0, dev ? std::atoi(dev) : 0), "DenseSLAMSystem");
+  g_last_map = map_;
+}
+
+DenseSLAMSystem::~DenseSLAMSystem() {
+  if (g_last_map == map_) g_last_map = nullptr;
+  se_b200_destroy(map_);
+}
+
+bool DenseSLAMSystem::preprocessing(const unsigned short* inputDepth, const Eigen::Vector2i& inputSize, bool /*filterInput*/) {
+  // mm2metersKernel (preprocessing.cpp:161-188); a bad ratio prints "Invalid ratio." and exits, as there
+  SE_CHECK(se_b200_preprocess_depth_host(map_, inputDepth, inputSize.x(), inputSize.y()), "preprocessing");
+  return true;
+}
+
+bool DenseSLAMSystem::tracking(const Eigen::Vector4f&, float, unsigned tracking_rate, unsigned frame) {
+  if (frame % tracking_rate != 0) return false;          // DenseSLAMSystem.cpp:146-147
+  static bool warned = false;
+  if (!warned) {
+    std::fprintf(stderr, "DenseSLAMSystem::tracking: ICP is not part of the GPU hot path yet (SURVEY.md N1); "
+                         "pose left unchanged -- supply poses with setPose()\n");
+    warned = true;
+  }
+  tracked_ = false;
+  return false;
+}
+
+bool DenseSLAMSystem::integration(const Eigen::Vector4f& k, unsigned integration_rate, float mu, unsigned frame) {
+  if (((frame % integration_rate) == 0) || (frame <= 3)) {   // DenseSLAMSystem.cpp:209
+    float p[16], kk[4];
+    pack(pose_, p); pack(k, kk);
+    SE_CHECK(se_b200_integrate(map_, p, kk, mu, frame), "integration");
+    integrated_ = true;
+    return true;
+  }
+  integrated_ = false;
+  return false;
+}
+
+bool DenseSLAMSystem::raycasting(const Eigen::Vector4f& k, float mu, unsigned frame) {
+  if (frame > 2) {                                            // DenseSLAMSystem.cpp:195
+    raycast_pose_ = pose_;
+    float p[16], kk[4];
+    pack(raycast_pose_, p); pack(k, kk);
+    SE_CHECK(se_b200_raycast(map_, p, kk, mu), "raycasting");
+    return true;
+  }
+  return false;
+}
+
+void DenseSLAMSystem::renderVolume(unsigned char* out, const Eigen::Vector2i&, int frame, int rate,
+                                   const Eigen::Vector4f& k, float largestep) {
+  if (frame % rate == 0) {                                    // DenseSLAMSystem.cpp:281
+    float p[16], kk[4];
+    pack(*viewPose_, p); pack(k, kk);
+    const int reraycast = !viewPose_->isApprox(raycast_pose_);   // :287
+    SE_CHECK(se_b200_render_volume_host(map_, out, p, kk, mu_, largestep, reraycast), "renderVolume");
+  }
+}
+
+void DenseSLAMSystem::renderTrack(unsigned char* out, const Eigen::Vector2i&) {
+  SE_CHECK(se_b200_render_track_host(map_, out, tracking_result_.data(), 8), "renderTrack");
+}
+
+void DenseSLAMSystem::renderDepth(unsigned char* out, const Eigen::Vector2i&) {
+  SE_CHECK(se_b200_render_depth_host(map_, out), "renderDepth");
+}
+
+void DenseSLAMSystem::dump_volume(const std::string) {}      // empty in the reference too (DenseSLAMSystem.cpp:270-272)
+
+void DenseSLAMSystem::dump_mesh(const std::string filename) {
+  std::fprintf(stderr, "DenseSLAMSystem::dump_mesh(%s): marching cubes is outside the GPU hot path (SURVEY.md N4)\n", filename.c_str());
+}
+
+void DenseSLAMSystem::getMap(std::shared_ptr<se::MapSnapshot>& out) {
+  auto s = std::make_shared<se::MapSnapshot>();
+  s->size = volume_resolution_.x();
+  s->dim = volume_dimension_.x();
+  int nb = 0, nn = 0;
+  SE_CHECK(se_b200_block_count(map_, &nb), "getMap");
+  SE_CHECK(se_b200_node_count(map_, &nn), "getMap");
+  s->block_keys.resize(nb); s->block_coords.resize((size_t)nb * 3); s->block_voxels.resize((size_t)nb * 512);
+  s->node_codes.resize(nn); s->node_sides.resize(nn); s->node_values.resize((size_t)nn * 8);
+  SE_CHECK(se_b200_download_blocks_sorted(map_, s->block_keys.data(), s->block_coords.data(), nullptr, s->block_voxels.data()), "getMap");
+  SE_CHECK(se_b200_download_nodes_sorted(map_, s->node_codes.data(), s->node_sides.data(), nullptr, s->node_values.data()), "getMap");
+  out = s;
+}
+
+void DenseSLAMSystem::getVertexNormal(std::vector<float>& vertex, std::vector<float>& normal) {
+  const size_t n = (size_t)computation_size_.x() * computation_size_.y() * 3;
+  vertex.resize(n); normal.resize(n);
+  SE_CHECK(se_b200_download_vertex_normal(map_, vertex.data(), normal.data()), "getVertexNormal");
+}
+
+float DenseSLAMSystem::stageMilliseconds(int stage) {
+  float ms = 0.f;
+  SE_CHECK(se_b200_elapsed_ms(map_, stage, &ms), "stageMilliseconds");
+  return ms;
+}
+
+void synchroniseDevices() { if (g_last_map) se_b200_sync(g_last_map); }

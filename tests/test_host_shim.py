@@ -1,0 +1,98 @@
+"""The C++ host side (supereight_b200/host): DenseSLAMSystem shim + frame-loop driver over the C ABI.
+CPU part: it builds and fails loudly without a device.  GPU part: a .raw stream driven through the shim with
+the reference's stage gates (benchmark.cpp:115-160) equals the oracle driven through the same gates."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from supereight_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "supereight_b200", "host")
+
+
+def exe(field):
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    return os.path.join(HOST, "_build", f"se-denseslam-{field}-b200-benchmark")
+
+
+def write_stream(tmp, frames, dim, W, H, k, scene="plane"):
+    raw = os.path.join(tmp, "scene.raw")
+    poses_path = os.path.join(tmp, "poses.txt")
+    depth, poses = [], []
+    with open(raw, "wb") as f, open(poses_path, "w") as g:
+        for i in range(frames):
+            d, p = (synth.planar_sweep if scene == "plane" else synth.box_room)(i, dim, W, H, k)
+            f.write(struct.pack("<II", W, H)); f.write(d.tobytes())
+            f.write(struct.pack("<II", W, H)); f.write(np.zeros((H, W, 3), np.uint8).tobytes())
+            g.write(" ".join(repr(float(v)) for v in p.reshape(-1)) + "\n")
+            depth.append(d); poses.append(p)
+    return raw, poses_path, depth, poses
+
+
+def read_dump(path, vdtype):
+    buf = open(path, "rb").read()
+    off, out = 0, []
+    for dt in (np.uint64, vdtype, np.uint64, vdtype, np.float32, np.float32, np.uint8, np.uint8, np.uint8):
+        n = struct.unpack_from("<Q", buf, off)[0]; off += 8
+        a = np.frombuffer(buf, dtype=dt, count=n, offset=off); off += n * np.dtype(dt).itemsize
+        out.append(a)
+    return out
+
+
+def test_host_side_builds_and_fails_loudly_without_gpu(tmp_path):
+    from supereight_b200 import capi
+    e = exe("sdf")
+    assert os.path.exists(e) and os.path.exists(exe("ofusion"))
+    if capi.load_library().se_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    raw, poses, _, _ = write_stream(str(tmp_path), 1, 4.8, 160, 120, (120.3, 120.0, 80.0, 60.0))
+    r = subprocess.run([e, "-i", raw, "-g", poses, "-k", "120.3,120,80,60"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field,mu", [("sdf", 0.1), ("ofusion", 0.008)])
+def test_shim_frame_loop_matches_oracle(tmp_path, field, mu):
+    W, H, size, dim, frames = 160, 120, 256, 4.8, 6
+    k = (120.3, 120.0, 80.0, 60.0)
+    raw, poses_path, depth, poses = write_stream(str(tmp_path), frames, dim, W, H, k)
+    dump = os.path.join(str(tmp_path), "dump.bin")
+    log = os.path.join(str(tmp_path), "log.tsv")
+    r = subprocess.run([exe(field), "-i", raw, "-g", poses_path, "-v", str(size), "-s", str(dim), "-m", str(mu), "-r", "2", "-z", "1",
+                        "-k", ",".join(str(v) for v in k), "-o", log, "-d", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split("\t") for ln in open(log).read().strip().split("\n")]
+    assert rows[0][0] == "frame" and len(rows) == frames + 1 and len(rows[1]) == 14
+    integrated = [int(rw[13]) for rw in rows[1:]]
+    assert integrated == [1, 1, 1, 1, 1, 0]                      # rate 2: frames 0..3 always, then even frames (DenseSLAMSystem.cpp:209)
+
+    fid = oracle_lib.SDF if field == "sdf" else oracle_lib.OFUSION
+    o = oracle_lib.Oracle(fid, size, dim, W, H)
+    for f in range(frames):
+        o.preprocess(depth[f])
+        if f % 2 == 0 or f <= 3:
+            o.integrate(poses[f], k, mu, f)
+        if f > 2:
+            o.raycast(poses[f], k, mu)
+    keys, _, _, data = o.blocks_sorted()
+    codes, _, _, values = o.nodes_sorted()
+    gk, gd, gc, gv, vert, norm, vol, dep, trk = read_dump(dump, o.vdtype)
+    assert np.array_equal(gk, keys) and np.array_equal(gc, codes)
+    gd = gd.reshape(-1, 512); gv = gv.reshape(-1, 8)
+    vert = vert.reshape(H, W, 3); norm = norm.reshape(H, W, 3)
+    if field == "sdf":
+        assert np.array_equal(gd["x"].view(np.uint32), data["x"].view(np.uint32)) and np.array_equal(gd["y"], data["y"])
+        assert np.array_equal(gv["x"].view(np.uint32), values["x"].view(np.uint32))
+        assert np.array_equal(vert.view(np.uint32), o.vertex().view(np.uint32))
+        assert np.array_equal(norm.view(np.uint32), o.normal().view(np.uint32))
+        assert np.array_equal(vol.reshape(H, W, 4), o.render_volume(poses[-1], k, mu, 0.75 * mu, False))
+    else:
+        np.testing.assert_allclose(gd["x"], data["x"], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(gd["y"], data["y"])
+    assert np.array_equal(dep.reshape(H, W, 4), o.render_depth())
+    assert np.all(trk.reshape(H, W, 4)[..., :3] == np.array([255, 128, 128], np.uint8))     # result 0 -> default colour (rendering.cpp:203-208)
