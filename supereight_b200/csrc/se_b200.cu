@@ -123,6 +123,9 @@ void make_bspline_lut(float lut[1000]) {
   }
 }
 
+// 0, or finite with magnitude in [2^-20, 2^20]
+bool normal_range(float v) { const float a = std::fabs(v); return v == 0.f || (a >= 0x1p-20f && a <= 0x1p20f); }
+
 int pixel_tile_blocks(int W, int H, int threads) {
   const int tiles = ((W + 7) / 8) * ((H + 3) / 4);
   const int warps_per_block = threads / 32;
@@ -225,14 +228,19 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   // counts read from device counters
   if (m->grid_integrate == 0) {
     int occ = 0;
-    const void* fn = FieldTraits<V>::is_sdf ? (const void*)k_integrate_sdf : (const void*)k_integrate_ofusion;
+    const void* fn = FieldTraits<V>::is_sdf ? (const void*)k_integrate_sdf<true> : (const void*)k_integrate_ofusion;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0) != cudaSuccess || occ < 1) occ = 2;
     m->grid_integrate = m->num_sms * occ;
   }
   k_active_list<V><<<m->num_sms * 2, threads, 0, m->stream>>>(view, fp, m->d_active_list);
-  if (FieldTraits<V>::is_sdf)
-    k_integrate_sdf<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
-  else
+  if (FieldTraits<V>::is_sdf) {
+    // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
+    // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
+    bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
+    for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
+    if (fast) k_integrate_sdf<true><<<m->grid_integrate, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
+    else k_integrate_sdf<false><<<m->grid_integrate, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
+  } else
     k_integrate_ofusion<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list);
   k_update_nodes<V><<<std::max(1, m->num_sms), threads, 0, m->stream>>>(view, m->d_depth, ip);
   if (int r = check_launch(m, 3)) return r;
