@@ -228,8 +228,13 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   // counts read from device counters
   if (m->grid_integrate == 0) {
     int occ = 0;
-    const void* fn = FieldTraits<V>::is_sdf ? (const void*)k_integrate_sdf<true> : (const void*)k_integrate_ofusion;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0) != cudaSuccess || occ < 1) occ = 2;
+    if (FieldTraits<V>::is_sdf) {
+      CUDA_TRY(cudaFuncSetAttribute(k_integrate_sdf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIntegrateSmem));
+      CUDA_TRY(cudaFuncSetAttribute(k_integrate_sdf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIntegrateSmem));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_sdf<true>, kIntegrateWarps * 32, kIntegrateSmem) != cudaSuccess || occ < 1) occ = 2;
+    } else {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_ofusion, threads, 0) != cudaSuccess || occ < 1) occ = 2;
+    }
     m->grid_integrate = m->num_sms * occ;
   }
   k_active_list<V><<<m->num_sms * 2, threads, 0, m->stream>>>(view, fp, m->d_active_list);
@@ -238,8 +243,8 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
     // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
     bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
     for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
-    if (fast) k_integrate_sdf<true><<<m->grid_integrate, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
-    else k_integrate_sdf<false><<<m->grid_integrate, threads, 0, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
+    if (fast) k_integrate_sdf<true><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
+    else k_integrate_sdf<false><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
   } else
     k_integrate_ofusion<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list);
   k_update_nodes<V><<<std::max(1, m->num_sms), threads, 0, m->stream>>>(view, m->d_depth, ip);
