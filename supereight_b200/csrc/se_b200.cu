@@ -73,6 +73,7 @@ struct se_b200_map {
   bool ev_valid[SE_B200_NUM_STAGES] = {};
   long long launches = 0;
   int grid_integrate = 0;
+  int parity = 0;
 
   template <class V> MapView<V> view() const {
     MapView<V> v;
@@ -168,6 +169,7 @@ int create_pools(se_b200_map* m) {
   const int one = 1;
   const unsigned side = (unsigned)m->size;
   CUDA_TRY(cudaMemcpyAsync(m->p.counters + kCntNodes, &one, sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(m->p.counters + kCntLastNodes, &one, sizeof(int), cudaMemcpyHostToDevice, m->stream));
   CUDA_TRY(cudaMemcpyAsync(m->p.node_side, &side, sizeof(unsigned), cudaMemcpyHostToDevice, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return SE_B200_OK;
@@ -197,8 +199,8 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
 
   // counters: remember the pool sizes before the frame, clear the per-frame ones
   stage_begin(m, SE_B200_STAGE_ALLOC);
-  k_frame_begin<<<1, 32, 0, m->stream>>>(m->p.counters);
-  if (int r = check_launch(m)) return r;
+  m->parity ^= 1;
+  const int parity = m->parity;
   const int threads = 256;
   const int grid_px = pixel_tile_blocks(m->W, m->H, threads);
   if (FieldTraits<V>::is_sdf) {
@@ -237,18 +239,17 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
     }
     m->grid_integrate = m->num_sms * occ;
   }
-  k_active_list<V><<<m->num_sms * 2, threads, 0, m->stream>>>(view, fp, m->d_active_list);
+  k_active_list<V><<<m->num_sms * 2, threads, 0, m->stream>>>(view, fp, m->d_active_list, parity);
   if (FieldTraits<V>::is_sdf) {
     // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
     // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
     bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
     for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
-    if (fast) k_integrate_sdf<true><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
-    else k_integrate_sdf<false><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list);
+    if (fast) k_integrate_sdf<true><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
+    else k_integrate_sdf<false><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
   } else
-    k_integrate_ofusion<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list);
-  k_update_nodes<V><<<std::max(1, m->num_sms), threads, 0, m->stream>>>(view, m->d_depth, ip);
-  if (int r = check_launch(m, 3)) return r;
+    k_integrate_ofusion<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity);
+  if (int r = check_launch(m, 2)) return r;
   stage_end(m, SE_B200_STAGE_FUSE);
   return SE_B200_OK;
 }
@@ -765,6 +766,9 @@ int se_b200_counters(se_b200_map* m, int32_t out[8]) {
   DeviceGuard guard(m->device);
   if (int r = fetch_counters(m)) return r;
   for (int i = 0; i < 8; ++i) out[i] = m->h_counters[i];
+  out[2] = m->h_counters[kCntActive0 + m->parity];
+  out[6] = m->h_counters[kCntKeysReport];
+  out[7] = 0;
   return check_pool_error(m);
 }
 

@@ -26,8 +26,11 @@ namespace se_b200 {
 constexpr int kEmpty = -1;
 constexpr int kBusy = -2;
 
-enum Counter { kCntNodes = 0, kCntBlocks = 1, kCntActive = 2, kCntError = 3, kCntNewBlocksBase = 4, kCntNewNodesBase = 5,
-               kCntKeys = 6, kCntScratch = 7, kNumCounters = 16 };
+// kCntActive0/1: the active-list length, double-buffered by frame parity (the list kernel of frame f counts into
+// slot f&1 and clears slot (f+1)&1 for the next frame -- no separate reset launch).
+enum Counter { kCntNodes = 0, kCntBlocks = 1, kCntError = 3, kCntNewBlocksBase = 4, kCntNewNodesBase = 5,
+               kCntKeys = 6, kCntKeysReport = 7, kCntActive0 = 8, kCntActive1 = 9, kCntLastBlocks = 10, kCntLastNodes = 11,
+               kNumCounters = 16 };
 enum ErrorBits { kErrBlockPoolFull = 1, kErrNodePoolFull = 2, kErrKeyListFull = 4 };
 
 // ---- field types (se_denseslam/include/se/volume_traits.hpp:41-72) --------------------
