@@ -84,8 +84,8 @@ int se_b200_integrate(se_b200_map* map, const float pose[16], const float k[4], 
 int se_b200_raycast(se_b200_map* map, const float pose[16], const float k[4], float mu);
 /* same raycast, additionally counting the field samples it takes: samples[0] = VolumeTemplate::get,
  * [1] = interp (8 voxels each), [2] = grad (32 distinct voxels each) -- the inputs of the
- * algorithmic-bytes figure of SURVEY.md 8(d).  Measurement only. */
-int se_b200_raycast_count_samples(se_b200_map* map, const float pose[16], const float k[4], float mu, uint64_t samples[3]);
+ * algorithmic-bytes figure of SURVEY.md 8(d) -- and [3] = octree walk steps.  Measurement only. */
+int se_b200_raycast_count_samples(se_b200_map* map, const float pose[16], const float k[4], float mu, uint64_t samples[4]);
 int se_b200_download_vertex_normal(se_b200_map* map, float* vertex, float* normal);   /* either may be NULL */
 int se_b200_upload_vertex_normal(se_b200_map* map, const float* vertex, const float* normal);
 

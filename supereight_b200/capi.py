@@ -152,9 +152,9 @@ class Map:
 
     def raycast_count_samples(self, pose, k, mu):
         p, kk = _f32(pose, 16), _f32(k, 4)
-        out = np.zeros(3, np.uint64)
+        out = np.zeros(4, np.uint64)
         self._check(self.lib.se_b200_raycast_count_samples(self.h, _ptr(p), _ptr(kk), mu, _ptr(out)))
-        return dict(n_get=int(out[0]), n_interp=int(out[1]), n_grad=int(out[2]))
+        return dict(n_get=int(out[0]), n_interp=int(out[1]), n_grad=int(out[2]), n_walk=int(out[3]))
 
     def vertex_normal(self):
         v = np.empty((self.H, self.W, 3), np.float32)

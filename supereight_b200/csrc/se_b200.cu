@@ -281,7 +281,8 @@ int render_volume_impl(se_b200_map* m, uchar4* out_dev, const float* view_pose, 
   const RaycastParams rp = make_raycast_params(m, view_pose, k, mu, kFarPlane * 2.0f, largestep, 0);   // DenseSLAMSystem.cpp:283-288
   const V3 light = v3(view_pose[3], view_pose[7], view_pose[11]);
   stage_begin(m, SE_B200_STAGE_RENDER);
-  k_render_volume<V><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, light, reraycast, m->d_vertex, m->d_normal, out_dev);
+  if (reraycast) k_render_volume<V><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
+  else k_render_shade<<<(m->W * m->H + 255) / 256, 256, 0, m->stream>>>(m->d_vertex, m->d_normal, light, m->W * m->H, out_dev);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RENDER);
   return SE_B200_OK;
@@ -532,15 +533,15 @@ int se_b200_raycast(se_b200_map* m, const float pose[16], const float k[4], floa
   return FIELD_DISPATCH(m, raycast_impl<SdfVoxel>(m, pose, k, mu, nullptr), raycast_impl<OfuVoxel>(m, pose, k, mu, nullptr));
 }
 
-int se_b200_raycast_count_samples(se_b200_map* m, const float pose[16], const float k[4], float mu, uint64_t samples[3]) {
+int se_b200_raycast_count_samples(se_b200_map* m, const float pose[16], const float k[4], float mu, uint64_t samples[4]) {
   REQUIRE_MAP(m);
   if (!pose || !k || !samples) return fail(SE_B200_ERR_ARG, "null argument");
   DeviceGuard guard(m->device);
   Scratch d;
-  CUDA_TRY(d.alloc(3 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemsetAsync(d.p, 0, 3 * sizeof(unsigned long long), m->stream));
+  CUDA_TRY(d.alloc(4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), m->stream));
   if (int r = FIELD_DISPATCH(m, raycast_impl<SdfVoxel>(m, pose, k, mu, (unsigned long long*)d.p), raycast_impl<OfuVoxel>(m, pose, k, mu, (unsigned long long*)d.p))) return r;
-  CUDA_TRY(cudaMemcpyAsync(samples, d.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(samples, d.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return SE_B200_OK;
 }

@@ -124,8 +124,8 @@ __device__ __forceinline__ int fetch_octant(const MapView<V>& m, int x, int y, i
 // this removes most root-to-leaf descents without changing any result.
 struct BlockCache {
   int bx, by, bz, idx;
-  int n_get, n_interp, n_grad;     // sample counters (SURVEY 8(d) algorithmic bytes); dead code unless a kernel reads them
-  __device__ __forceinline__ BlockCache() : bx(-1), by(-1), bz(-1), idx(kEmpty), n_get(0), n_interp(0), n_grad(0) {}
+  int n_get, n_interp, n_grad, n_walk;     // sample counters (SURVEY 8(d) algorithmic bytes); dead code unless a kernel reads them
+  __device__ __forceinline__ BlockCache() : bx(-1), by(-1), bz(-1), idx(kEmpty), n_get(0), n_interp(0), n_grad(0), n_walk(0) {}
 };
 template <class V>
 __device__ __forceinline__ int fetch_block_cached(const MapView<V>& m, BlockCache& c, int x, int y, int z) {
