@@ -182,6 +182,24 @@ def run_cpu(cfg, depth, poses, k, warmup, steps, budget_s=25.0):
 
 
 # ------------------------------------------------------------------------------------------------
+# N > 1: replicas only -- the one "collective" is a MAX over ranks of the timed durations
+# ------------------------------------------------------------------------------------------------
+def max_over_ranks(values_ms, world, device=None):
+    """all_reduce(MAX) of per-rank durations (works on nccl with a cuda device and on gloo with cpu)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values_ms), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def aggregate_value(world, steps, max_ms):
+    """whole-job throughput: units all ranks processed / the slowest rank's time"""
+    return world * steps / (max_ms * 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args, cfg, rank, world, local_rank):
@@ -275,10 +293,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
     m.close()
 
     # ---------------- aggregate: max over ranks ----------------
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_ms_max, e2e_ms_max = max_over_ranks([total_ms, e2e_s * 1e3], world, dev)
     result = None
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -299,7 +314,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
         frame_bytes = sum(ab.values())
         frame_ms = sum(kernels[s]["ms"] for s in stages)
         result = {
-            "metric": METRIC, "value": round(world * steps / (total_ms_max * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": round(aggregate_value(world, steps, total_ms_max), 2), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": round(total_ms_max / steps, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "field": "SDF" if cfg["field"] == 0 else "OFusion", "volume": f"{cfg['size']}^3 @ {cfg['dim']} m",
@@ -307,7 +322,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
                        "stages": "mm2meters+alloc+integrate+raycast+renderVolume(reuse)", "poses": "supplied (no tracking)",
                        "parallelism": f"replicas x{world} (one map per GPU)", "l2": "flushed between timed steps (256 MiB write)",
                        "blocks": counters["blocks"], "active_blocks": counters["active"], "nodes": counters["nodes"]},
-            "e2e": {"value": round(world * steps / (e2e_ms_max * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": W * H * 2,
+            "e2e": {"value": round(aggregate_value(world, steps, e2e_ms_max), 2), "unit": UNIT, "h2d_bytes_per_step": W * H * 2,
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(e2e_ms_max / steps, 5), "result_checksum": checksum},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
