@@ -110,6 +110,11 @@ int se_b200_block_count(se_b200_map* map, int* out);
 int se_b200_node_count(se_b200_map* map, int* out);
 int se_b200_download_blocks_sorted(se_b200_map* map, uint64_t* keys, int32_t* coords_xyz, uint8_t* active, void* voxels);
 int se_b200_download_nodes_sorted(se_b200_map* map, uint64_t* codes, uint32_t* side, uint8_t* children_mask, void* values);
+/* Octree::load (octree.hpp:917-950): re-create nodes / blocks from saved records -- insert(coords, level)
+ * followed by a copy of value_[8] / the 512-voxel payload.  keys/codes carry the level in their low 9 bits as
+ * written by Octree::save; `voxels` is n*512 payload structs, `values` n*8.  Either call may be used alone. */
+int se_b200_upload_blocks(se_b200_map* map, const uint64_t* keys, const void* voxels, int n);
+int se_b200_upload_nodes(se_b200_map* map, const uint64_t* codes, const void* values, int n);
 /* Octree::allocate for an explicit key list (octree.hpp:792-817), incl. multi-level keys */
 int se_b200_allocate_keys(se_b200_map* map, const uint64_t* keys, int n);
 /* point queries, n points each: get_fine (octree.hpp:356-377) at integer voxels, interp

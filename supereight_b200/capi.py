@@ -22,7 +22,7 @@ EXPORTS = (
     "se_b200_integrate", "se_b200_raycast", "se_b200_raycast_count_samples", "se_b200_download_vertex_normal", "se_b200_upload_vertex_normal",
     "se_b200_render_volume_host", "se_b200_render_volume_device", "se_b200_render_depth_host",
     "se_b200_render_track_host", "se_b200_block_count", "se_b200_node_count", "se_b200_download_blocks_sorted",
-    "se_b200_download_nodes_sorted", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
+    "se_b200_download_nodes_sorted", "se_b200_upload_blocks", "se_b200_upload_nodes", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
     "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_counters",
     "se_b200_launch_count", "se_b200_device_image",
 )
@@ -69,6 +69,8 @@ def load_library():
     lib.se_b200_download_blocks_sorted.argtypes = [vp, vp, vp, vp, vp]
     lib.se_b200_download_nodes_sorted.argtypes = [vp, vp, vp, vp, vp]
     lib.se_b200_allocate_keys.argtypes = [vp, vp, i32]
+    lib.se_b200_upload_blocks.argtypes = [vp, vp, vp, i32]
+    lib.se_b200_upload_nodes.argtypes = [vp, vp, vp, i32]
     lib.se_b200_query_voxels.argtypes = [vp, vp, i32, vp]
     lib.se_b200_query_interp.argtypes = [vp, vp, i32, vp]
     lib.se_b200_query_grad.argtypes = [vp, vp, i32, vp]
@@ -220,6 +222,16 @@ class Map:
         values = np.empty((n, 8), self.vdtype)
         self._check(self.lib.se_b200_download_nodes_sorted(self.h, _ptr(codes), _ptr(side), _ptr(mask), _ptr(values)))
         return codes, side, mask, values
+
+    def upload_blocks(self, keys, voxels):
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        v = np.ascontiguousarray(voxels, dtype=self.vdtype).reshape(len(k), 512)
+        self._check(self.lib.se_b200_upload_blocks(self.h, _ptr(k), _ptr(v), len(k)))
+
+    def upload_nodes(self, codes, values):
+        k = np.ascontiguousarray(codes, dtype=np.uint64)
+        v = np.ascontiguousarray(values, dtype=self.vdtype).reshape(len(k), 8)
+        self._check(self.lib.se_b200_upload_nodes(self.h, _ptr(k), _ptr(v), len(k)))
 
     def allocate(self, keys):
         k = np.ascontiguousarray(keys, dtype=np.uint64)

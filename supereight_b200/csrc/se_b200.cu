@@ -669,6 +669,43 @@ int se_b200_allocate_keys(se_b200_map* m, const uint64_t* keys, int n) {
   return check_pool_error(m);
 }
 
+int se_b200_upload_blocks(se_b200_map* m, const uint64_t* keys, const void* voxels, int n) {
+  REQUIRE_MAP(m);
+  if (n < 0 || (n > 0 && (!keys || !voxels))) return fail(SE_B200_ERR_ARG, "bad block list");
+  if (n == 0) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  Scratch dk, dv;
+  const size_t vbytes = (size_t)n * kBlockVoxels * m->voxel_bytes;
+  CUDA_TRY(dk.alloc((size_t)n * sizeof(unsigned long long)));
+  CUDA_TRY(dv.alloc(vbytes));
+  CUDA_TRY(cudaMemcpyAsync(dk.p, keys, (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(dv.p, voxels, vbytes, cudaMemcpyHostToDevice, m->stream));
+  const int blocks = (n * 32 + 255) / 256;
+  if (m->field == SE_B200_SDF) k_upload_blocks<SdfVoxel><<<blocks, 256, 0, m->stream>>>(m->view<SdfVoxel>(), (unsigned long long*)dk.p, (SdfVoxel*)dv.p, n);
+  else k_upload_blocks<OfuVoxel><<<blocks, 256, 0, m->stream>>>(m->view<OfuVoxel>(), (unsigned long long*)dk.p, (OfuVoxel*)dv.p, n);
+  if (int r = check_launch(m)) return r;
+  if (int r = fetch_counters(m)) return r;
+  return check_pool_error(m);
+}
+
+int se_b200_upload_nodes(se_b200_map* m, const uint64_t* codes, const void* values, int n) {
+  REQUIRE_MAP(m);
+  if (n < 0 || (n > 0 && (!codes || !values))) return fail(SE_B200_ERR_ARG, "bad node list");
+  if (n == 0) return SE_B200_OK;
+  DeviceGuard guard(m->device);
+  Scratch dk, dv;
+  const size_t vbytes = (size_t)n * 8 * m->voxel_bytes;
+  CUDA_TRY(dk.alloc((size_t)n * sizeof(unsigned long long)));
+  CUDA_TRY(dv.alloc(vbytes));
+  CUDA_TRY(cudaMemcpyAsync(dk.p, codes, (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(dv.p, values, vbytes, cudaMemcpyHostToDevice, m->stream));
+  if (m->field == SE_B200_SDF) k_upload_nodes<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (unsigned long long*)dk.p, (SdfVoxel*)dv.p, n);
+  else k_upload_nodes<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (unsigned long long*)dk.p, (OfuVoxel*)dv.p, n);
+  if (int r = check_launch(m)) return r;
+  if (int r = fetch_counters(m)) return r;
+  return check_pool_error(m);
+}
+
 int se_b200_query_voxels(se_b200_map* m, const int32_t* xyz, int n, void* out) {
   REQUIRE_MAP(m);
   if (n <= 0) return SE_B200_OK;

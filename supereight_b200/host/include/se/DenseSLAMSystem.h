@@ -43,6 +43,12 @@ struct MapSnapshot {                                   // what Octree::save writ
   std::vector<uint64_t> node_codes;
   std::vector<uint32_t> node_sides;
   std::vector<FieldType> node_values;                  // 8 per node
+  // The file format of Octree::save / Octree::load (se_core/include/se/octree.hpp:897-950,
+  // io/se_serialise.hpp:54-99): int size, float dim, size_t n_nodes, {u64 code, u32 side, value_[8]} x n,
+  // size_t n_blocks, {u64 code, int3 coords, voxel[512]} x n.  Records are written in key order (the
+  // reference writes pool order, which is arbitrary there too).
+  bool save(const std::string& filename) const;
+  bool load(const std::string& filename);
 };
 }  // namespace se
 
@@ -80,6 +86,8 @@ class DenseSLAMSystem {
   void renderDepth(unsigned char* out, const Eigen::Vector2i& outputSize);   // :285
 
   void getMap(std::shared_ptr<se::MapSnapshot>& out);                         // :295 (see header comment)
+  // inverse of getMap(): rebuild the device map from a snapshot (the role of Octree::load, octree.hpp:917-950)
+  void setMap(const se::MapSnapshot& in);
   bool getTracked() { return tracked_; }
   bool getIntegrated() { return integrated_; }
   Eigen::Vector3f getPosition() {                                             // :318-325

@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <type_traits>
 
 #include "se_b200.h"
@@ -138,6 +139,56 @@ void DenseSLAMSystem::getMap(std::shared_ptr<se::MapSnapshot>& out) {
   SE_CHECK(se_b200_download_blocks_sorted(map_, s->block_keys.data(), s->block_coords.data(), nullptr, s->block_voxels.data()), "getMap");
   SE_CHECK(se_b200_download_nodes_sorted(map_, s->node_codes.data(), s->node_sides.data(), nullptr, s->node_values.data()), "getMap");
   out = s;
+}
+
+void DenseSLAMSystem::setMap(const se::MapSnapshot& in) {
+  SE_CHECK(se_b200_upload_nodes(map_, in.node_codes.data(), in.node_values.data(), (int)in.node_codes.size()), "setMap");
+  SE_CHECK(se_b200_upload_blocks(map_, in.block_keys.data(), in.block_voxels.data(), (int)in.block_keys.size()), "setMap");
+}
+
+bool se::MapSnapshot::save(const std::string& filename) const {
+  std::ofstream os(filename, std::ios::binary);
+  if (!os) return false;
+  os.write((const char*)&size, sizeof(int));
+  os.write((const char*)&dim, sizeof(float));
+  size_t n = node_codes.size();
+  os.write((const char*)&n, sizeof(size_t));
+  for (size_t i = 0; i < n; ++i) {
+    os.write((const char*)&node_codes[i], sizeof(uint64_t));
+    os.write((const char*)&node_sides[i], sizeof(uint32_t));
+    os.write((const char*)&node_values[8 * i], sizeof(FieldType) * 8);
+  }
+  n = block_keys.size();
+  os.write((const char*)&n, sizeof(size_t));
+  for (size_t i = 0; i < n; ++i) {
+    os.write((const char*)&block_keys[i], sizeof(uint64_t));
+    os.write((const char*)&block_coords[3 * i], sizeof(int32_t) * 3);
+    os.write((const char*)&block_voxels[512 * i], sizeof(FieldType) * 512);
+  }
+  return (bool)os;
+}
+
+bool se::MapSnapshot::load(const std::string& filename) {
+  std::ifstream is(filename, std::ios::binary);
+  if (!is) return false;
+  is.read((char*)&size, sizeof(int));
+  is.read((char*)&dim, sizeof(float));       // the reference reads dim into an int (octree.hpp:921-923); the file holds a float
+  size_t n = 0;
+  is.read((char*)&n, sizeof(size_t));
+  node_codes.resize(n); node_sides.resize(n); node_values.resize(8 * n);
+  for (size_t i = 0; i < n; ++i) {
+    is.read((char*)&node_codes[i], sizeof(uint64_t));
+    is.read((char*)&node_sides[i], sizeof(uint32_t));
+    is.read((char*)&node_values[8 * i], sizeof(FieldType) * 8);
+  }
+  is.read((char*)&n, sizeof(size_t));
+  block_keys.resize(n); block_coords.resize(3 * n); block_voxels.resize(512 * n);
+  for (size_t i = 0; i < n; ++i) {
+    is.read((char*)&block_keys[i], sizeof(uint64_t));
+    is.read((char*)&block_coords[3 * i], sizeof(int32_t) * 3);
+    is.read((char*)&block_voxels[512 * i], sizeof(FieldType) * 512);
+  }
+  return (bool)is;
 }
 
 void DenseSLAMSystem::getVertexNormal(std::vector<float>& vertex, std::vector<float>& normal) {

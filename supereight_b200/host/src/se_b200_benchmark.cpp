@@ -6,7 +6,7 @@
 // se_apps/src/mainQt.cpp:257-265; poses are relative to the initial position, as setPose expects).
 //
 //   se-denseslam-{sdf,ofusion}-b200-benchmark -i scene.raw -g poses.txt [-v 512] [-s 4.8] [-m 0.1] [-c 1]
-//        [-r 1] [-z 1] [-p 0,0,0] [-k fx,fy,cx,cy] [-o log.tsv] [-d dump.bin] [-n max_frames]
+//        [-r 1] [-z 1] [-p 0,0,0] [-k fx,fy,cx,cy] [-o log.tsv] [-d dump.bin] [-b map.bin] [-n max_frames]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
   config.camera = Eigen::Vector4f(481.2f, 480.f, 320.f, 240.f);
   config.pyramid = {10, 5, 4};
   config.integration_rate = 2; config.rendering_rate = 4; config.mu = 0.1f; config.compute_size_ratio = 1;
-  std::string poses_file, dump_file;
+  std::string poses_file, dump_file, map_file;
   int max_frames = -1;
   for (int i = 1; i + 1 < argc; i += 2) {
     const std::string a = argv[i]; const char* v = argv[i + 1];
@@ -76,6 +76,7 @@ int main(int argc, char** argv) {
     else if (a == "-z") config.rendering_rate = std::atoi(v);
     else if (a == "-o") config.log_file = v;
     else if (a == "-d") dump_file = v;
+    else if (a == "-b") map_file = v;
     else if (a == "-n") max_frames = std::atoi(v);
     else if (a == "-p") { auto p = parse_floats(v); if (p.size() == 3) config.initial_pos_factor = Eigen::Vector3f(p[0], p[1], p[2]); }
     else if (a == "-k") { auto p = parse_floats(v); if (p.size() == 4) { config.camera = Eigen::Vector4f(p[0], p[1], p[2], p[3]); config.camera_overrided = true; } }
@@ -133,6 +134,23 @@ int main(int argc, char** argv) {
                << s(t[5], t[6]) << "\t" << s(t[1], t[5]) << "\t" << s(t[0], t[6]) << "\t" << xt << "\t" << yt << "\t" << zt << "\t" << tracked << "        \t" << integrated << std::endl;
     frame++;
     t[0] = clk::now();
+  }
+  if (!map_file.empty()) {                                  // benchmark.cpp:179-181 writes "test.bin" the same way
+    std::shared_ptr<se::MapSnapshot> map;
+    pipeline.getMap(map);
+    if (!map->save(map_file)) { std::cerr << "cannot write " << map_file << std::endl; return 1; }
+    // round trip: load the file into a fresh pipeline and check it reproduces the same snapshot
+    se::MapSnapshot back;
+    if (!back.load(map_file)) { std::cerr << "cannot read back " << map_file << std::endl; return 1; }
+    DenseSLAMSystem second(Eigen::Vector2i(cw, ch), config.volume_resolution, config.volume_size, init_pose, config.pyramid, config);
+    second.setMap(back);
+    std::shared_ptr<se::MapSnapshot> again;
+    second.getMap(again);
+    const bool same = again->block_keys == map->block_keys && again->node_codes == map->node_codes &&
+                      std::memcmp(again->block_voxels.data(), map->block_voxels.data(), map->block_voxels.size() * sizeof(FieldType)) == 0 &&
+                      std::memcmp(again->node_values.data(), map->node_values.data(), map->node_values.size() * sizeof(FieldType)) == 0;
+    std::cerr << "map file round trip: " << (same ? "identical" : "DIFFERENT") << " (" << map->block_keys.size() << " blocks, " << map->node_codes.size() << " nodes)" << std::endl;
+    if (!same) return 3;
   }
   if (!dump_file.empty()) {                                 // parity artefact for tests/test_gpu_host_shim.py
     std::shared_ptr<se::MapSnapshot> map;

@@ -331,3 +331,29 @@ def test_error_paths_and_render_track():
     small.preprocess(d); small.integrate(pose, scaled_k(160), 0.1, 0)
     with pytest.raises(SeB200Error, match="pool exhausted"):
         small.block_count()
+
+
+@pytest.mark.parametrize("field,mu", [(SDF, 0.1), (OFUSION, 0.008)])
+def test_map_export_import_round_trip(field, mu):
+    """Octree::save -> Octree::load (octree.hpp:897-950) through the ABI: a map rebuilt from its exported records
+    is the same map (same keys, same payloads, same raycast)."""
+    from supereight_b200 import Map, synth
+    dim, W, H = 4.8, 160, 120
+    k = scaled_k(W)
+    a = Map(field, 256, dim, W, H)
+    for f in range(3):
+        d, pose = synth.planar_sweep(f, dim, W, H, k)
+        a.preprocess(d); a.integrate(pose, k, mu, f)
+    keys, coords, active, data = a.blocks_sorted()
+    codes, side, mask, values = a.nodes_sorted()
+    b = Map(field, 256, dim, W, H)
+    b.upload_nodes(codes, values)
+    b.upload_blocks(keys, data)
+    keys2, coords2, _, data2 = b.blocks_sorted()
+    codes2, side2, mask2, values2 = b.nodes_sorted()
+    assert np.array_equal(keys, keys2) and np.array_equal(coords, coords2) and data.tobytes() == data2.tobytes()
+    assert np.array_equal(codes, codes2) and np.array_equal(side, side2) and np.array_equal(mask, mask2)
+    assert values.tobytes() == values2.tobytes()
+    a.raycast(pose, k, mu); b.raycast(pose, k, mu)
+    va, na = a.vertex_normal(); vb, nb = b.vertex_normal()
+    assert va.tobytes() == vb.tobytes() and na.tobytes() == nb.tobytes()

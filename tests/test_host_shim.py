@@ -63,9 +63,13 @@ def test_shim_frame_loop_matches_oracle(tmp_path, field, mu):
     raw, poses_path, depth, poses = write_stream(str(tmp_path), frames, dim, W, H, k)
     dump = os.path.join(str(tmp_path), "dump.bin")
     log = os.path.join(str(tmp_path), "log.tsv")
+    mapfile = os.path.join(str(tmp_path), "test.bin")
     r = subprocess.run([exe(field), "-i", raw, "-g", poses_path, "-v", str(size), "-s", str(dim), "-m", str(mu), "-r", "2", "-z", "1",
-                        "-k", ",".join(str(v) for v in k), "-o", log, "-d", dump], capture_output=True, text=True)
+                        "-k", ",".join(str(v) for v in k), "-o", log, "-d", dump, "-b", mapfile], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    assert "map file round trip: identical" in r.stderr          # Octree::save format written, loaded into a fresh map, re-exported
+    hdr = struct.unpack_from("<ifQ", open(mapfile, "rb").read(16))
+    assert hdr[0] == size and abs(hdr[1] - dim) < 1e-6 and hdr[2] > 1
     rows = [ln.split("\t") for ln in open(log).read().strip().split("\n")]
     assert rows[0][0] == "frame" and len(rows) == frames + 1 and len(rows[1]) == 14
     integrated = [int(rw[13]) for rw in rows[1:]]
