@@ -94,13 +94,32 @@ int se_b200_upload_vertex_normal(se_b200_map* map, const float* vertex, const fl
  * the reference (benchmark.cpp:90-97).  reraycast != 0 is the reference's `render` flag (view
  * pose differs from the raycast pose: cast again from the volume entry with far plane 8 m);
  * 0 shades the stored vertex/normal maps.  light = translation of view_pose.
- * track_result: W*H ints `stride_ints` apart (TrackData::result, commons.h:249-253 -> stride 8). */
+ * track_result: W*H ints `stride_ints` apart (TrackData::result, commons.h:249-253 -> stride 8);
+ * NULL = the TrackData the last se_b200_track left on the device. */
 int se_b200_render_volume_host(se_b200_map* map, uint8_t* out, const float view_pose[16], const float k[4],
                                float mu, float largestep, int reraycast);
 int se_b200_render_volume_device(se_b200_map* map, uint8_t* out_dev, const float view_pose[16], const float k[4],
                                  float mu, float largestep, int reraycast);
 int se_b200_render_depth_host(se_b200_map* map, uint8_t* out);
 int se_b200_render_track_host(se_b200_map* map, uint8_t* out, const int* track_result, int stride_ints);
+
+/* ---- N1: the tracking front-end either side of the hot path ----------------
+ * se_b200_filter_depth = second half of DenseSLAMSystem::preprocessing (DenseSLAMSystem.cpp:132-139):
+ *   bilateralFilterKernel (preprocessing.cpp:42-87) when filter != 0, else a copy, into level 0 of the
+ *   depth pyramid; call it after se_b200_preprocess_depth_*.  `levels` = pyramid depth (config.pyramid.size()).
+ * se_b200_track = the body of DenseSLAMSystem::tracking (DenseSLAMSystem.cpp:149-188): half-sample pyramid,
+ *   depth2vertex / vertex2normal per level (preprocessing.cpp:89-226), then per level `iterations[level]` rounds
+ *   of trackKernel + reduceKernel (tracking.cpp:66-300) on the GPU and the 6x6 solve + SE3 exponential
+ *   (tracking.cpp:302-318) on the host, against the vertex / normal maps of the last se_b200_raycast taken from
+ *   `raycast_pose`; finally checkPoseKernel (:320-336).  pose_io is updated in place (restored when the check
+ *   fails), *tracked = the check's verdict.  se_b200_render_track_host(map, out, NULL, 0) renders its result. */
+int se_b200_filter_depth(se_b200_map* map, int filter, int levels);
+int se_b200_track(se_b200_map* map, float pose_io[16], const float raycast_pose[16], const float k[4], float icp_threshold,
+                  const int* iterations, int levels, int* tracked);
+/* inspection: one pyramid level (depth (W>>l)*(H>>l), vertex / normal 3 floats per pixel) and the TrackData image
+ * (W*H records of 8 x 4 bytes: int result, float error, float J[6]) + the 32 reduced sums of the last iteration */
+int se_b200_download_pyramid(se_b200_map* map, int level, float* depth, float* vertex, float* normal);
+int se_b200_download_tracking(se_b200_map* map, void* track_data, float reduction[32]);
 
 /* ---- inspection: what getMap() / Octree::save expose in the reference --------------------
  * (DenseSLAMSystem.h:295-297, octree.hpp:897-915).  Pool order is arbitrary in the reference

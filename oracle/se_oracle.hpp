@@ -715,6 +715,200 @@ static inline float bspline_memoized(float t) {          // mapping_impl.hpp:126
 static inline float h_new(float val) { return bspline_memoized(val) - bspline_memoized(val - 3) * 0.5f; } // :139-143
 
 // ----------------------------------------------------------------------------
+// N1: tracking front-end.  preprocessing.cpp:42-159,190-226, tracking.cpp:42-336,
+// DenseSLAMSystem.cpp:143-189.  The float reductions of the reference are OpenMP reductions
+// (order not defined); here they are serial per row block, so this oracle is deterministic and
+// the GPU path is compared with a tolerance, not bit for bit.
+// ----------------------------------------------------------------------------
+struct TrackData { int result; float error; float J[6]; };      // commons.h:249-253
+
+constexpr float kEDelta = 0.1f;              // constant_parameters.h:17
+constexpr int   kRadius = 2;                 // :18
+constexpr float kDistThreshold = 0.1f;       // :19
+constexpr float kNormalThreshold = 0.8f;     // :20
+constexpr float kTrackThreshold = 0.15f;     // :21
+constexpr float kGaussDelta = 4.0f;          // :34
+
+// DenseSLAMSystem.cpp:111-118
+static inline void make_gaussian(float g[5]) { for (int i = 0; i < 5; ++i) { const int x = i - 2; g[i] = std::exp(-(float)(x * x) / (2 * kGaussDelta * kGaussDelta)); } }
+
+// preprocessing.cpp:42-87
+static inline void bilateral_filter(std::vector<float>& out, const std::vector<float>& in, int W, int H) {
+  float g[5]; make_gaussian(g);
+  const float e_d_squared_2 = kEDelta * kEDelta * 2;
+  const int r = kRadius;
+#pragma omp parallel for
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const int pos = x + y * W;
+      if (in[pos] == 0) { out[pos] = 0; continue; }
+      float sum = 0.f, t = 0.f;
+      const float center = in[pos];
+      for (int i = -r; i <= r; ++i)
+        for (int j = -r; j <= r; ++j) {
+          const int cx = std::max(0, std::min(x + i, W - 1)), cy = std::max(0, std::min(y + j, H - 1));
+          const float curPix = in[cx + cy * W];
+          if (curPix > 0) {
+            const float mod = (curPix - center) * (curPix - center);
+            const float factor = g[i + r] * g[j + r] * std::exp(-mod / e_d_squared_2);
+            t += factor * curPix;
+            sum += factor;
+          }
+        }
+      out[pos] = t / sum;
+    }
+}
+// preprocessing.cpp:190-226 (r = 1, e_d = 3 * e_delta at the call site, DenseSLAMSystem.cpp:151)
+static inline void half_sample_robust(std::vector<float>& out, const std::vector<float>& in, int outW, int outH, float e_d, int r) {
+  const int inW = outW * 2;
+#pragma omp parallel for
+  for (int y = 0; y < outH; ++y)
+    for (int x = 0; x < outW; ++x) {
+      const int cx = 2 * x, cy = 2 * y;
+      float sum = 0.f, t = 0.f;
+      const float center = in[cx + cy * inW];
+      for (int i = -r + 1; i <= r; ++i)
+        for (int j = -r + 1; j <= r; ++j) {
+          const int px = std::min(std::max(cx + j, 0), 2 * outW - 1), py = std::min(std::max(cy + i, 0), 2 * outH - 1);
+          const float current = in[px + py * inW];
+          if (std::fabs(current - center) < e_d) { sum += 1.0f; t += current; }
+        }
+      out[x + y * outW] = t / sum;
+    }
+}
+// preprocessing.cpp:89-109 : depth * invK * (x, y, 1, 0)
+static inline void depth2vertex(std::vector<V3>& vertex, const std::vector<float>& depth, int W, int H, const M4& invK) {
+#pragma omp parallel for
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const float d = depth[x + y * W];
+      if (d > 0) {
+        // (depth * invK) * v : the scalar multiplies the matrix first (Eigen evaluates left to right)
+        V3 r;
+        const float vx = (float)x, vy = (float)y;
+        r.x = ((d * invK.at(0,0)) * vx + (d * invK.at(0,1)) * vy) + (d * invK.at(0,2)) * 1.f;
+        r.y = ((d * invK.at(1,0)) * vx + (d * invK.at(1,1)) * vy) + (d * invK.at(1,2)) * 1.f;
+        r.z = ((d * invK.at(2,0)) * vx + (d * invK.at(2,1)) * vy) + (d * invK.at(2,2)) * 1.f;
+        vertex[x + y * W] = r;
+      } else vertex[x + y * W] = {0, 0, 0};
+    }
+}
+static inline V3 cross3(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+// preprocessing.cpp:111-159 ; only .x is written for invalid pixels (the rest keeps its old value)
+static inline void vertex2normal(std::vector<V3>& out, const std::vector<V3>& in, int W, int H, bool negY) {
+#pragma omp parallel for
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const V3 center = in[x + W * y];
+      if (center.z == 0.f) { out[x + y * W].x = kInvalid; continue; }
+      const int xl = std::max(x - 1, 0), xr = std::min(x + 1, W - 1);
+      int yu, yd;
+      if (negY) { yu = std::max(y - 1, 0); yd = std::min(y + 1, H - 1); }
+      else { yd = std::max(y - 1, 0); yu = std::min(y + 1, H - 1); }
+      const V3 left = in[xl + W * y], right = in[xr + W * y], up = in[x + W * yu], down = in[x + W * yd];
+      if (left.z == 0 || right.z == 0 || up.z == 0 || down.z == 0) { out[x + y * W].x = kInvalid; continue; }
+      out[x + y * W] = normalized3(cross3(right - left, up - down));
+    }
+}
+// tracking.cpp:226-300
+static inline void track_kernel(TrackData* output, const std::vector<V3>& inVertex, const std::vector<V3>& inNormal, int inW, int inH,
+                                const std::vector<V3>& refVertex, const std::vector<V3>& refNormal, int refW, int refH,
+                                const M4& Ttrack, const M4& view, float dist_threshold, float normal_threshold) {
+#pragma omp parallel for
+  for (int py = 0; py < inH; ++py)
+    for (int px = 0; px < inW; ++px) {
+      TrackData& row = output[px + py * refW];
+      const V3 inN = inNormal[px + py * inW];
+      if (inN.x == kInvalid) { row.result = -1; continue; }
+      const V3 projectedVertex = xform3(Ttrack, inVertex[px + py * inW]);
+      const V3 projectedPos = xform3(view, projectedVertex);
+      const float ppx = projectedPos.x / projectedPos.z + 0.5f, ppy = projectedPos.y / projectedPos.z + 0.5f;
+      if (ppx < 0 || ppx > refW - 1 || ppy < 0 || ppy > refH - 1) { row.result = -2; continue; }
+      const int rx = (int)ppx, ry = (int)ppy;
+      const V3 referenceNormal = refNormal[rx + ry * refW];
+      if (referenceNormal.x == kInvalid) { row.result = -3; continue; }
+      const V3 diff = refVertex[rx + ry * refW] - projectedVertex;
+      const V3 projectedNormal = rot3(Ttrack, inN);
+      if (norm3(diff) > dist_threshold) { row.result = -4; continue; }
+      if (dot3(projectedNormal, referenceNormal) < normal_threshold) { row.result = -5; continue; }
+      row.result = 1;
+      row.error = dot3(referenceNormal, diff);
+      row.J[0] = referenceNormal.x; row.J[1] = referenceNormal.y; row.J[2] = referenceNormal.z;
+      const V3 c = cross3(projectedVertex, referenceNormal);
+      row.J[3] = c.x; row.J[4] = c.y; row.J[5] = c.z;
+    }
+}
+// tracking.cpp:66-224 : 8 interleaved row blocks, 32 sums each, then the 8 rows added into row 0
+static inline void reduce_kernel(float* out /*8*32*/, const TrackData* J, int JW, int W, int H) {
+#pragma omp parallel for
+  for (int blockIndex = 0; blockIndex < 8; ++blockIndex) {
+    float s[32];
+    for (float& v : s) v = 0.f;
+    for (int y = blockIndex; y < H; y += 8)
+      for (int x = 0; x < W; ++x) {
+        const TrackData& row = J[x + y * JW];
+        if (row.result < 1) {
+          s[29] += row.result == -4 ? 1 : 0;
+          s[30] += row.result == -5 ? 1 : 0;
+          s[31] += row.result > -4 ? 1 : 0;
+          continue;
+        }
+        s[0] += row.error * row.error;
+        for (int i = 0; i < 6; ++i) s[1 + i] += row.error * row.J[i];
+        int k = 7;
+        for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) s[k++] += row.J[i] * row.J[j];
+        s[28] += 1;
+      }
+    for (int i = 0; i < 32; ++i) out[blockIndex * 32 + i] = s[i];
+  }
+  for (int j = 1; j < 8; ++j) for (int i = 0; i < 32; ++i) out[i] += out[j * 32 + i];
+}
+// 6x6 Cholesky solve (tracking.cpp:57-64 uses Eigen::LLT); false when not positive definite
+static inline bool solve6(const float* vals /*27: b[6], upper JTJ[21]*/, float x[6]) {
+  float C[6][6], L[6][6] = {};
+  int k = 6;
+  for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { C[i][j] = vals[k]; C[j][i] = vals[k]; ++k; }
+  for (int j = 0; j < 6; ++j) {
+    float d = C[j][j];
+    for (int t = 0; t < j; ++t) d -= L[j][t] * L[j][t];
+    if (!(d > 0.f)) return false;
+    L[j][j] = std::sqrt(d);
+    for (int i = j + 1; i < 6; ++i) {
+      float v = C[i][j];
+      for (int t = 0; t < j; ++t) v -= L[i][t] * L[j][t];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  float y[6];
+  for (int i = 0; i < 6; ++i) { float v = vals[i]; for (int t = 0; t < i; ++t) v -= L[i][t] * y[t]; y[i] = v / L[i][i]; }
+  for (int i = 5; i >= 0; --i) { float v = y[i]; for (int t = i + 1; t < 6; ++t) v -= L[t][i] * x[t]; x[i] = v / L[i][i]; }
+  return true;
+}
+// Sophus::SE3f::exp(x), x = (upsilon, omega): closed form (Rodrigues + V matrix)
+static inline M4 se3_exp(const float x[6]) {
+  const float wx = x[3], wy = x[4], wz = x[5];
+  const float theta2 = wx * wx + wy * wy + wz * wz, theta = std::sqrt(theta2);
+  float A, B, Cc;        // sin(t)/t, (1-cos t)/t^2, (t - sin t)/t^3
+  if (theta < 1e-4f) { A = 1.f - theta2 / 6.f; B = 0.5f - theta2 / 24.f; Cc = 1.f / 6.f - theta2 / 120.f; }
+  else { A = std::sin(theta) / theta; B = (1.f - std::cos(theta)) / theta2; Cc = (theta - std::sin(theta)) / (theta2 * theta); }
+  const float W[3][3] = {{0, -wz, wy}, {wz, 0, -wx}, {-wy, wx, 0}};
+  float W2[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { W2[i][j] = 0; for (int t = 0; t < 3; ++t) W2[i][j] += W[i][t] * W[t][j]; }
+  M4 T{};
+  for (int i = 0; i < 3; ++i) {
+    float tv = 0;
+    for (int j = 0; j < 3; ++j) {
+      const float I = i == j ? 1.f : 0.f;
+      T.at(i, j) = I + A * W[i][j] + B * W2[i][j];
+      tv += (I + B * W[i][j] + Cc * W2[i][j]) * x[j];
+    }
+    T.at(i, 3) = tv;
+  }
+  T.at(3, 3) = 1.f;
+  return T;
+}
+
+// ----------------------------------------------------------------------------
 // the pipeline state the hot path touches (DenseSLAMSystem.h:61-93)
 // ----------------------------------------------------------------------------
 template <class F> struct Pipeline {
@@ -973,6 +1167,56 @@ template <class F> struct Pipeline {
 #pragma omp parallel for
     for (int i = 0; i < nn; ++i) update_node(map.nodes[i], voxelsize, Tcw, K, mu, timestamp);
     return allocated;
+  }
+
+  // ---- N1: DenseSLAMSystem::preprocessing (filter) + ::tracking (DenseSLAMSystem.cpp:128-189) ----
+  std::vector<std::vector<float>> scaled_depth;
+  std::vector<std::vector<V3>> input_vertex, input_normal;
+  std::vector<TrackData> tracking_result;
+  float reduction[8 * 32];
+  void ensure_pyramid(int levels) {
+    if ((int)scaled_depth.size() == levels) return;
+    scaled_depth.assign(levels, {}); input_vertex.assign(levels, {}); input_normal.assign(levels, {});
+    for (int i = 0; i < levels; ++i) {
+      const size_t n = (size_t)(W >> i) * (H >> i);
+      scaled_depth[i].assign(n, 0.f); input_vertex[i].assign(n, V3{0, 0, 0}); input_normal[i].assign(n, V3{0, 0, 0});
+    }
+    tracking_result.assign((size_t)W * H, TrackData{0, 0.f, {0, 0, 0, 0, 0, 0}});
+  }
+  // second half of preprocessing(): bilateral filter or plain copy into scaled_depth_[0]
+  void filter_depth(bool filter, int levels) {
+    ensure_pyramid(levels);
+    if (filter) bilateral_filter(scaled_depth[0], depth, W, H);
+    else scaled_depth[0] = depth;
+  }
+  // tracking(): pose is updated in place; returns checkPoseKernel's verdict.  raycast_pose = pose of the
+  // vertex/normal maps (raycast_pose_).  iterations[level] as Configuration::pyramid.
+  bool tracking(M4& pose, const M4& raycast_pose, const float k[4], float icp_threshold, const int* iterations, int levels) {
+    ensure_pyramid(levels);
+    for (int i = 1; i < levels; ++i) half_sample_robust(scaled_depth[i], scaled_depth[i - 1], W >> i, H >> i, kEDelta * 3, 1);
+    for (int i = 0; i < levels; ++i) {
+      const float ks[4] = { k[0] / (float)(1 << i), k[1] / (float)(1 << i), k[2] / (float)(1 << i), k[3] / (float)(1 << i) };
+      depth2vertex(input_vertex[i], scaled_depth[i], W >> i, H >> i, inverse_camera_matrix(ks));
+      vertex2normal(input_normal[i], input_vertex[i], W >> i, H >> i, k[1] < 0);
+    }
+    const M4 old_pose = pose;
+    const M4 projectReference = mul44(camera_matrix(k), rigid_inverse(raycast_pose));
+    for (int level = levels - 1; level >= 0; --level) {
+      const int lw = W / (1 << level), lh = H / (1 << level);
+      for (int i = 0; i < iterations[level]; ++i) {
+        track_kernel(tracking_result.data(), input_vertex[level], input_normal[level], lw, lh, vertex, normal, W, H, pose, projectReference,
+                     kDistThreshold, kNormalThreshold);
+        reduce_kernel(reduction, tracking_result.data(), W, lw, lh);
+        float x[6];
+        if (!solve6(reduction + 1, x)) for (float& v : x) v = 0.f;
+        pose = mul44(se3_exp(x), pose);
+        float n2 = 0; for (float v : x) n2 += v * v;
+        if (std::sqrt(n2) < icp_threshold) break;
+      }
+    }
+    // checkPoseKernel (tracking.cpp:320-336)
+    if ((std::sqrt(reduction[0] / reduction[28]) > 2e-2) || (reduction[28] / (float)(W * H) < kTrackThreshold)) { pose = old_pose; return false; }
+    return true;
   }
 
   // a13: rendering.cpp:50-90 ; view = raycast_pose * K^-1

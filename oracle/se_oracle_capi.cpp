@@ -161,6 +161,29 @@ int seo_ray_blocks(void* h, const float* origin, const float* dir, float nearP, 
   return n;
 }
 
+// ---- N1 ----------------------------------------------------------------------
+void seo_filter_depth(void* h, int filter, int levels) { DISPATCH(h, P.filter_depth(filter != 0, levels)); }
+int seo_tracking(void* h, float* pose_io, const float* raycast_pose, const float* k, float icp_threshold, const int* iterations, int levels) {
+  int r = 0;
+  DISPATCH(h, { M4 p = to_m4(pose_io); r = P.tracking(p, to_m4(raycast_pose), k, icp_threshold, iterations, levels) ? 1 : 0; std::memcpy(pose_io, p.m, sizeof(p.m)); });
+  return r;
+}
+void seo_get_pyramid(void* h, int level, float* depth, float* vertex, float* normal) {
+  DISPATCH(h, {
+    if (depth) std::memcpy(depth, P.scaled_depth[level].data(), sizeof(float) * P.scaled_depth[level].size());
+    if (vertex) std::memcpy(vertex, P.input_vertex[level].data(), sizeof(V3) * P.input_vertex[level].size());
+    if (normal) std::memcpy(normal, P.input_normal[level].data(), sizeof(V3) * P.input_normal[level].size());
+  });
+}
+void seo_get_tracking(void* h, void* track_data /*W*H*32 B*/, float* reduction /*32*/) {
+  DISPATCH(h, {
+    if (track_data) std::memcpy(track_data, P.tracking_result.data(), sizeof(TrackData) * P.tracking_result.size());
+    if (reduction) std::memcpy(reduction, P.reduction, sizeof(float) * 32);
+  });
+}
+void seo_se3_exp(const float x[6], float out[16]) { M4 t = se3_exp(x); std::memcpy(out, t.m, sizeof(t.m)); }
+int seo_solve6(const float vals[27], float x[6]) { return solve6(vals, x) ? 1 : 0; }
+
 void seo_set_counting(void* h, int on) { DISPATCH(h, P.count = on != 0); }
 void seo_reset_counters(void* h) { DISPATCH(h, P.ctr = Counters()); }
 void seo_get_counters(void* h, uint64_t out[9]) {

@@ -21,7 +21,8 @@ EXPORTS = (
     "se_b200_sync", "se_b200_preprocess_depth_host", "se_b200_preprocess_depth_device", "se_b200_set_depth_m_host",
     "se_b200_integrate", "se_b200_raycast", "se_b200_raycast_count_samples", "se_b200_download_vertex_normal", "se_b200_upload_vertex_normal",
     "se_b200_render_volume_host", "se_b200_render_volume_device", "se_b200_render_depth_host",
-    "se_b200_render_track_host", "se_b200_block_count", "se_b200_node_count", "se_b200_download_blocks_sorted",
+    "se_b200_render_track_host", "se_b200_filter_depth", "se_b200_track", "se_b200_download_pyramid",
+    "se_b200_download_tracking", "se_b200_block_count", "se_b200_node_count", "se_b200_download_blocks_sorted",
     "se_b200_download_nodes_sorted", "se_b200_upload_blocks", "se_b200_upload_nodes", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
     "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_counters",
     "se_b200_launch_count", "se_b200_device_image",
@@ -64,6 +65,10 @@ def load_library():
     lib.se_b200_render_volume_device.argtypes = [vp, vp, vp, vp, f32, f32, i32]
     lib.se_b200_render_depth_host.argtypes = [vp, vp]
     lib.se_b200_render_track_host.argtypes = [vp, vp, vp, i32]
+    lib.se_b200_filter_depth.argtypes = [vp, i32, i32]
+    lib.se_b200_track.argtypes = [vp, vp, vp, vp, f32, vp, i32, C.POINTER(i32)]
+    lib.se_b200_download_pyramid.argtypes = [vp, i32, vp, vp, vp]
+    lib.se_b200_download_tracking.argtypes = [vp, vp, vp]
     lib.se_b200_block_count.argtypes = [vp, C.POINTER(i32)]
     lib.se_b200_node_count.argtypes = [vp, C.POINTER(i32)]
     lib.se_b200_download_blocks_sorted.argtypes = [vp, vp, vp, vp, vp]
@@ -192,6 +197,36 @@ class Map:
         r = np.ascontiguousarray(result, dtype=np.int32)
         out = np.empty((self.H, self.W, 4), np.uint8)
         self._check(self.lib.se_b200_render_track_host(self.h, _ptr(out), _ptr(r), stride_ints))
+        return out
+
+    # ---- N1: tracking front-end ---------------------------------------------------------
+    def filter_depth(self, filter: bool, levels: int = 3):
+        self._check(self.lib.se_b200_filter_depth(self.h, int(filter), levels))
+
+    def track(self, pose, raycast_pose, k, icp_threshold, iterations):
+        """Returns (new_pose [4,4] float32, tracked bool)."""
+        p = _f32(pose, 16).reshape(4, 4).copy()
+        rp, kk = _f32(raycast_pose, 16), _f32(k, 4)
+        it = np.ascontiguousarray(iterations, dtype=np.int32)
+        ok = C.c_int()
+        self._check(self.lib.se_b200_track(self.h, _ptr(p), _ptr(rp), _ptr(kk), icp_threshold, _ptr(it), len(it), C.byref(ok)))
+        return p, bool(ok.value)
+
+    def pyramid(self, level):
+        w, h = self.W >> level, self.H >> level
+        d = np.empty((h, w), np.float32); v = np.empty((h, w, 3), np.float32); n = np.empty((h, w, 3), np.float32)
+        self._check(self.lib.se_b200_download_pyramid(self.h, level, _ptr(d), _ptr(v), _ptr(n)))
+        return d, v, n
+
+    def tracking_data(self):
+        td = np.empty((self.H, self.W), np.dtype([("result", "<i4"), ("error", "<f4"), ("J", "<f4", (6,))]))
+        red = np.zeros(32, np.float32)
+        self._check(self.lib.se_b200_download_tracking(self.h, _ptr(td), _ptr(red)))
+        return td, red
+
+    def render_track_last(self):
+        out = np.empty((self.H, self.W, 4), np.uint8)
+        self._check(self.lib.se_b200_render_track_host(self.h, _ptr(out), None, 0))
         return out
 
     # ---- inspection -----------------------------------------------------------------------

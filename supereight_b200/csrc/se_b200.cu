@@ -7,6 +7,7 @@
 // -fmad=false / -ffp-contract=off are part of the arithmetic contract (se_math.cuh).
 #include "../../include/se_b200.h"
 #include "se_kernels.cuh"
+#include "se_tracking.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -67,6 +68,15 @@ struct se_b200_map {
   unsigned long long* d_requests = nullptr;
   int* d_track = nullptr;
   size_t track_capacity = 0;
+  // N1 (tracking front-end): depth pyramid, per-level vertex/normal maps, TrackData, reduction scratch
+  int levels = 0;
+  float* d_scaled_depth[8] = {};
+  float* d_in_vertex[8] = {};
+  float* d_in_normal[8] = {};
+  TrackData* d_trackdata = nullptr;
+  float* d_partial = nullptr;
+  float* d_reduction = nullptr;
+  float* h_reduction = nullptr;          // pinned, 32 floats
   int* h_counters = nullptr;              // pinned
   cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev_begin[SE_B200_NUM_STAGES] = {}, ev_end[SE_B200_NUM_STAGES] = {};
@@ -90,6 +100,8 @@ struct se_b200_map {
 };
 
 namespace {
+
+int ensure_tracking_buffers(se_b200_map* m, int levels);     // N1, defined with the tracking entry points below
 
 struct DeviceGuard {
   int prev = -1;
@@ -442,6 +454,9 @@ int se_b200_destroy(se_b200_map* m) {
   cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir);
   cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
   cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_track);
+  for (int i = 0; i < 8; ++i) { cudaFree(m->d_scaled_depth[i]); cudaFree(m->d_in_vertex[i]); cudaFree(m->d_in_normal[i]); }
+  cudaFree(m->d_trackdata); cudaFree(m->d_partial); cudaFree(m->d_reduction);
+  if (m->h_reduction) cudaFreeHost(m->h_reduction);
   if (m->h_counters) cudaFreeHost(m->h_counters);
   for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { if (m->ev_begin[i]) cudaEventDestroy(m->ev_begin[i]); if (m->ev_end[i]) cudaEventDestroy(m->ev_end[i]); }
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -600,9 +615,17 @@ int se_b200_render_depth_host(se_b200_map* m, uint8_t* out) {
 
 int se_b200_render_track_host(se_b200_map* m, uint8_t* out, const int* track_result, int stride_ints) {
   REQUIRE_MAP(m);
-  if (!out || !track_result || stride_ints < 1) return fail(SE_B200_ERR_ARG, "bad argument");
+  if (!out || (track_result && stride_ints < 1)) return fail(SE_B200_ERR_ARG, "bad argument");
   DeviceGuard guard(m->device);
   const int n = m->W * m->H;
+  if (!track_result) {              // the result of the last se_b200_track, already on the device
+    if (!m->d_trackdata) { if (int r = ensure_tracking_buffers(m, 1)) return r; }
+    k_render_track<<<(n + 255) / 256, 256, 0, m->stream>>>(m->d_rgba, (const int*)m->d_trackdata, (int)(sizeof(TrackData) / sizeof(int)), n);
+    if (int r = check_launch(m)) return r;
+    CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return SE_B200_OK;
+  }
   const size_t bytes = (size_t)n * stride_ints * sizeof(int);
   if (m->track_capacity < bytes) {
     CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -825,6 +848,179 @@ int se_b200_device_image(se_b200_map* m, int which, void** ptr) {
     case 2: *ptr = m->d_normal; break;
     default: return fail(SE_B200_ERR_ARG, "which must be 0..2");
   }
+  return SE_B200_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// N1: tracking front-end
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int ensure_tracking_buffers(se_b200_map* m, int levels) {
+  if (levels < 1 || levels > 8) return fail(SE_B200_ERR_ARG, "pyramid levels must be in [1, 8]");
+  if ((m->W >> (levels - 1)) < 1 || (m->H >> (levels - 1)) < 1) return fail(SE_B200_ERR_ARG, "too many pyramid levels for this image size");
+  for (int i = 0; i < levels; ++i) {
+    if (m->d_scaled_depth[i]) continue;
+    const size_t n = (size_t)(m->W >> i) * (m->H >> i);
+    CUDA_TRY(cudaMalloc(&m->d_scaled_depth[i], n * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->d_in_vertex[i], n * 3 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->d_in_normal[i], n * 3 * sizeof(float)));
+    CUDA_TRY(cudaMemsetAsync(m->d_scaled_depth[i], 0, n * sizeof(float), m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->d_in_vertex[i], 0, n * 3 * sizeof(float), m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->d_in_normal[i], 0, n * 3 * sizeof(float), m->stream));
+  }
+  if (!m->d_trackdata) {
+    const size_t n = (size_t)m->W * m->H;
+    CUDA_TRY(cudaMalloc(&m->d_trackdata, n * sizeof(TrackData)));
+    CUDA_TRY(cudaMemsetAsync(m->d_trackdata, 0, n * sizeof(TrackData), m->stream));
+    CUDA_TRY(cudaMalloc(&m->d_partial, ((n + kTrackThreads - 1) / kTrackThreads) * 32 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->d_reduction, 32 * sizeof(float)));
+    CUDA_TRY(cudaMallocHost(&m->h_reduction, 32 * sizeof(float)));
+    std::memset(m->h_reduction, 0, 32 * sizeof(float));
+  }
+  m->levels = std::max(m->levels, levels);
+  return SE_B200_OK;
+}
+
+// 6x6 Cholesky solve of (J^T J) x = J^T e; vals = b[6] followed by the upper triangle (tracking.cpp:42-64, Eigen::LLT there)
+bool solve6(const float* vals, float x[6]) {
+  float C[6][6], L[6][6] = {};
+  int k = 6;
+  for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { C[i][j] = vals[k]; C[j][i] = vals[k]; ++k; }
+  for (int j = 0; j < 6; ++j) {
+    float d = C[j][j];
+    for (int t = 0; t < j; ++t) d -= L[j][t] * L[j][t];
+    if (!(d > 0.f)) return false;
+    L[j][j] = std::sqrt(d);
+    for (int i = j + 1; i < 6; ++i) {
+      float v = C[i][j];
+      for (int t = 0; t < j; ++t) v -= L[i][t] * L[j][t];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  float y[6];
+  for (int i = 0; i < 6; ++i) { float v = vals[i]; for (int t = 0; t < i; ++t) v -= L[i][t] * y[t]; y[i] = v / L[i][i]; }
+  for (int i = 5; i >= 0; --i) { float v = y[i]; for (int t = i + 1; t < 6; ++t) v -= L[t][i] * x[t]; x[i] = v / L[i][i]; }
+  return true;
+}
+
+// exp: se(3) -> SE(3), x = (upsilon, omega), Rodrigues + V matrix (Sophus::SE3f::exp at tracking.cpp:310)
+M4 se3_exp(const float x[6]) {
+  const float wx = x[3], wy = x[4], wz = x[5];
+  const float theta2 = wx * wx + wy * wy + wz * wz, theta = std::sqrt(theta2);
+  float A, B, Cc;
+  if (theta < 1e-4f) { A = 1.f - theta2 / 6.f; B = 0.5f - theta2 / 24.f; Cc = 1.f / 6.f - theta2 / 120.f; }
+  else { A = std::sin(theta) / theta; B = (1.f - std::cos(theta)) / theta2; Cc = (theta - std::sin(theta)) / (theta2 * theta); }
+  const float W[3][3] = {{0, -wz, wy}, {wz, 0, -wx}, {-wy, wx, 0}};
+  float W2[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { W2[i][j] = 0; for (int t = 0; t < 3; ++t) W2[i][j] += W[i][t] * W[t][j]; }
+  M4 T; for (float& f : T.m) f = 0.f;
+  for (int i = 0; i < 3; ++i) {
+    float tv = 0;
+    for (int j = 0; j < 3; ++j) {
+      const float I = i == j ? 1.f : 0.f;
+      T.m[4 * i + j] = I + A * W[i][j] + B * W2[i][j];
+      tv += (I + B * W[i][j] + Cc * W2[i][j]) * x[j];
+    }
+    T.m[4 * i + 3] = tv;
+  }
+  T.m[15] = 1.f;
+  return T;
+}
+
+dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
+
+}  // namespace
+
+extern "C" {
+
+int se_b200_filter_depth(se_b200_map* m, int filter, int levels) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  if (int r = ensure_tracking_buffers(m, levels)) return r;
+  if (filter) {
+    Gauss5 gs;
+    for (int i = 0; i < 5; ++i) { const int x = i - 2; gs.g[i] = expf(-(float)(x * x) / (2 * kGaussDelta * kGaussDelta)); }   // DenseSLAMSystem.cpp:111-118
+    k_bilateral<<<grid2d(m->W, m->H), dim3(32, 8), 0, m->stream>>>(m->d_scaled_depth[0], m->d_depth, m->W, m->H, gs);
+    if (int r = check_launch(m)) return r;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(m->d_scaled_depth[0], m->d_depth, (size_t)m->W * m->H * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+  }
+  return SE_B200_OK;
+}
+
+int se_b200_track(se_b200_map* m, float pose_io[16], const float raycast_pose[16], const float k[4], float icp_threshold,
+                  const int* iterations, int levels, int* tracked) {
+  REQUIRE_MAP(m);
+  if (!pose_io || !raycast_pose || !k || !iterations) return fail(SE_B200_ERR_ARG, "null argument");
+  DeviceGuard guard(m->device);
+  if (int r = ensure_tracking_buffers(m, levels)) return r;
+  const dim3 tb(32, 8);
+  // pyramid + per-level vertex / normal maps (DenseSLAMSystem.cpp:149-164)
+  for (int i = 1; i < levels; ++i)
+    k_half_sample<<<grid2d(m->W >> i, m->H >> i), tb, 0, m->stream>>>(m->d_scaled_depth[i], m->d_scaled_depth[i - 1], m->W >> i, m->H >> i, kEDelta * 3, 1);
+  for (int i = 0; i < levels; ++i) {
+    const float s = (float)(1 << i);
+    const float ks[4] = { k[0] / s, k[1] / s, k[2] / s, k[3] / s };
+    k_depth2vertex<<<grid2d(m->W >> i, m->H >> i), tb, 0, m->stream>>>(m->d_in_vertex[i], m->d_scaled_depth[i], m->W >> i, m->H >> i, inverse_camera_matrix(ks));
+    k_vertex2normal<<<grid2d(m->W >> i, m->H >> i), tb, 0, m->stream>>>(m->d_in_normal[i], m->d_in_vertex[i], m->W >> i, m->H >> i, k[1] < 0 ? 1 : 0);
+  }
+  if (int r = check_launch(m, 3 * levels - 1)) return r;
+
+  M4 pose = to_m4(pose_io);
+  const M4 old_pose = pose;
+  TrackParams tp;
+  tp.view = mul44(camera_matrix(k), rigid_inverse(to_m4(raycast_pose)));          // projectReference, :167
+  tp.refW = m->W; tp.refH = m->H; tp.dist_threshold = kDistThreshold; tp.normal_threshold = kNormalThreshold;
+  for (int level = levels - 1; level >= 0; --level) {
+    tp.inW = m->W / (1 << level); tp.inH = m->H / (1 << level);
+    const int n = tp.inW * tp.inH, ctas = (n + kTrackThreads - 1) / kTrackThreads;
+    for (int i = 0; i < iterations[level]; ++i) {
+      tp.Ttrack = pose;
+      k_track<<<ctas, kTrackThreads, 0, m->stream>>>(m->d_trackdata, m->d_in_vertex[level], m->d_in_normal[level], m->d_vertex, m->d_normal, tp, m->d_partial);
+      k_reduce_final<<<1, 256, 0, m->stream>>>(m->d_partial, ctas, m->d_reduction);
+      if (int r = check_launch(m, 2)) return r;
+      CUDA_TRY(cudaMemcpyAsync(m->h_reduction, m->d_reduction, 32 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+      CUDA_TRY(cudaStreamSynchronize(m->stream));
+      // updatePoseKernel (tracking.cpp:302-318)
+      float x[6];
+      if (!solve6(m->h_reduction + 1, x)) for (float& v : x) v = 0.f;
+      pose = mul44(se3_exp(x), pose);
+      float n2 = 0.f;
+      for (float v : x) n2 += v * v;
+      if (std::sqrt(n2) < icp_threshold) break;
+    }
+  }
+  // checkPoseKernel (tracking.cpp:320-336)
+  const float* v = m->h_reduction;
+  bool ok = true;
+  if ((std::sqrt(v[0] / v[28]) > 2e-2) || (v[28] / (float)(m->W * m->H) < kTrackThreshold)) { pose = old_pose; ok = false; }
+  std::memcpy(pose_io, pose.m, sizeof(pose.m));
+  if (tracked) *tracked = ok ? 1 : 0;
+  return SE_B200_OK;
+}
+
+int se_b200_download_pyramid(se_b200_map* m, int level, float* depth, float* vertex, float* normal) {
+  REQUIRE_MAP(m);
+  if (level < 0 || level >= m->levels || !m->d_scaled_depth[level]) return fail(SE_B200_ERR_ARG, "pyramid level not built");
+  DeviceGuard guard(m->device);
+  const size_t n = (size_t)(m->W >> level) * (m->H >> level);
+  if (depth) CUDA_TRY(cudaMemcpyAsync(depth, m->d_scaled_depth[level], n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  if (vertex) CUDA_TRY(cudaMemcpyAsync(vertex, m->d_in_vertex[level], n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  if (normal) CUDA_TRY(cudaMemcpyAsync(normal, m->d_in_normal[level], n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_download_tracking(se_b200_map* m, void* track_data, float reduction[32]) {
+  REQUIRE_MAP(m);
+  if (!m->d_trackdata) return fail(SE_B200_ERR_ARG, "tracking has not run");
+  DeviceGuard guard(m->device);
+  if (track_data) CUDA_TRY(cudaMemcpyAsync(track_data, m->d_trackdata, (size_t)m->W * m->H * sizeof(TrackData), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (reduction) std::memcpy(reduction, m->h_reduction, 32 * sizeof(float));
   return SE_B200_OK;
 }
 

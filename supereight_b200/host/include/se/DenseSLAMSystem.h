@@ -10,9 +10,9 @@
 //  * getMap() cannot hand out a host se::Octree (the map is in HBM): it returns a snapshot
 //    (se::MapSnapshot: blocks and nodes sorted by key, the comparable form of Octree::save,
 //    se_core/include/se/octree.hpp:897-915).
-//  * tracking() (ICP) is not on the GPU path yet: it returns false and leaves the
-//    pose untouched; supply poses with setPose() (the reference's ground-truth mode,
-//    se_apps/src/mainQt.cpp:257-265).
+//  * tracking() runs the ICP residual / reduction kernels on the GPU and the 6x6 solve + SE3
+//    exponential on the host; its float reductions have a fixed order, so results are
+//    reproducible but equal to the CPU reference only to rounding.
 //  * errors the reference handles with exit(1) (bad size ratio, preprocessing.cpp:165-176)
 //    do the same here, with the library's message.
 #pragma once
@@ -70,7 +70,7 @@ class DenseSLAMSystem {
 
   // :147  mm -> m (+ sub-sampling to the computation size); `filterInput` only feeds tracking (N1)
   bool preprocessing(const unsigned short* inputDepth, const Eigen::Vector2i& inputSize, bool filterInput);
-  // :173  see the header comment
+  // :173  ICP against the last raycast; returns checkPoseKernel's verdict (pose restored when it fails)
   bool tracking(const Eigen::Vector4f& k, float icp_threshold, unsigned tracking_rate, unsigned frame);
   // :193  runs when frame % integration_rate == 0 or frame <= 3 (DenseSLAMSystem.cpp:209)
   bool integration(const Eigen::Vector4f& k, unsigned integration_rate, float mu, unsigned frame);
@@ -129,7 +129,6 @@ class DenseSLAMSystem {
   bool need_render_ = false;
   Configuration config_;
   Eigen::Matrix4f raycast_pose_;
-  std::vector<int> tracking_result_;          // TrackData (8 ints per pixel, commons.h:249-253)
   se_b200_map* map_ = nullptr;
 };
 

@@ -50,7 +50,6 @@ DenseSLAMSystem::DenseSLAMSystem(const Eigen::Vector2i& inputSize, const Eigen::
   raycast_pose_ = initPose;
   iterations_ = pyramid;
   viewPose_ = &pose_;
-  tracking_result_.assign((size_t)inputSize.x() * inputSize.y() * 8, 0);
   const char* dev = std::getenv("SE_B200_DEVICE");
   SE_CHECK(se_b200_create(&map_, kFieldType, volumeResolution.x(), volumeDimensions.x(), inputSize.x(), inputSize.y(),
                           0, 0, dev ? std::atoi(dev) : 0), "DenseSLAMSystem");
@@ -62,22 +61,24 @@ DenseSLAMSystem::~DenseSLAMSystem() {
   se_b200_destroy(map_);
 }
 
-bool DenseSLAMSystem::preprocessing(const unsigned short* inputDepth, const Eigen::Vector2i& inputSize, bool /*filterInput*/) {
+bool DenseSLAMSystem::preprocessing(const unsigned short* inputDepth, const Eigen::Vector2i& inputSize, bool filterInput) {
   // mm2metersKernel (preprocessing.cpp:161-188); a bad ratio prints "Invalid ratio." and exits, as there
   SE_CHECK(se_b200_preprocess_depth_host(map_, inputDepth, inputSize.x(), inputSize.y()), "preprocessing");
+  // bilateralFilterKernel or a plain copy into scaled_depth_[0] (DenseSLAMSystem.cpp:132-139)
+  if (!iterations_.empty()) SE_CHECK(se_b200_filter_depth(map_, filterInput ? 1 : 0, (int)iterations_.size()), "preprocessing");
   return true;
 }
 
-bool DenseSLAMSystem::tracking(const Eigen::Vector4f&, float, unsigned tracking_rate, unsigned frame) {
+bool DenseSLAMSystem::tracking(const Eigen::Vector4f& k, float icp_threshold, unsigned tracking_rate, unsigned frame) {
   if (frame % tracking_rate != 0) return false;          // DenseSLAMSystem.cpp:146-147
-  static bool warned = false;
-  if (!warned) {
-    std::fprintf(stderr, "DenseSLAMSystem::tracking: ICP is not part of the GPU hot path yet (SURVEY.md N1); "
-                         "pose left unchanged -- supply poses with setPose()\n");
-    warned = true;
-  }
-  tracked_ = false;
-  return false;
+  if (iterations_.empty()) return false;
+  float p[16], rp[16], kk[4];
+  pack(pose_, p); pack(raycast_pose_, rp); pack(k, kk);
+  int ok = 0;
+  SE_CHECK(se_b200_track(map_, p, rp, kk, icp_threshold, iterations_.data(), (int)iterations_.size(), &ok), "tracking");
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) pose_(r, c) = p[4 * r + c];
+  tracked_ = ok != 0;
+  return tracked_;
 }
 
 bool DenseSLAMSystem::integration(const Eigen::Vector4f& k, unsigned integration_rate, float mu, unsigned frame) {
@@ -114,7 +115,7 @@ void DenseSLAMSystem::renderVolume(unsigned char* out, const Eigen::Vector2i&, i
 }
 
 void DenseSLAMSystem::renderTrack(unsigned char* out, const Eigen::Vector2i&) {
-  SE_CHECK(se_b200_render_track_host(map_, out, tracking_result_.data(), 8), "renderTrack");
+  SE_CHECK(se_b200_render_track_host(map_, out, nullptr, 0), "renderTrack");     // the TrackData of the last tracking(), on the device
 }
 
 void DenseSLAMSystem::renderDepth(unsigned char* out, const Eigen::Vector2i&) {

@@ -6,7 +6,7 @@
 // se_apps/src/mainQt.cpp:257-265; poses are relative to the initial position, as setPose expects).
 //
 //   se-denseslam-{sdf,ofusion}-b200-benchmark -i scene.raw -g poses.txt [-v 512] [-s 4.8] [-m 0.1] [-c 1]
-//        [-r 1] [-z 1] [-p 0,0,0] [-k fx,fy,cx,cy] [-o log.tsv] [-d dump.bin] [-b map.bin] [-n max_frames]
+//        [-r 1] [-z 1] [-p 0,0,0] [-k fx,fy,cx,cy] [-o log.tsv] [-d dump.bin] [-b map.bin] [-n max_frames] [-t 0|1] [-f 0|1]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +64,7 @@ int main(int argc, char** argv) {
   config.integration_rate = 2; config.rendering_rate = 4; config.mu = 0.1f; config.compute_size_ratio = 1;
   std::string poses_file, dump_file, map_file;
   int max_frames = -1;
+  bool use_tracking = false;      // -t 1: track with ICP after the first 4 frames instead of reading the pose file
   for (int i = 1; i + 1 < argc; i += 2) {
     const std::string a = argv[i]; const char* v = argv[i + 1];
     if (a == "-i") config.input_file = v;
@@ -78,6 +79,8 @@ int main(int argc, char** argv) {
     else if (a == "-d") dump_file = v;
     else if (a == "-b") map_file = v;
     else if (a == "-n") max_frames = std::atoi(v);
+    else if (a == "-t") use_tracking = std::atoi(v) != 0;
+    else if (a == "-f") config.bilateralFilter = std::atoi(v) != 0;
     else if (a == "-p") { auto p = parse_floats(v); if (p.size() == 3) config.initial_pos_factor = Eigen::Vector3f(p[0], p[1], p[2]); }
     else if (a == "-k") { auto p = parse_floats(v); if (p.size() == 4) { config.camera = Eigen::Vector4f(p[0], p[1], p[2], p[3]); config.camera_overrided = true; } }
     else { std::cerr << "unknown option " << a << std::endl; return 2; }
@@ -113,8 +116,9 @@ int main(int argc, char** argv) {
     pipeline.preprocessing(inputDepth.data(), Eigen::Vector2i((int)reader.w, (int)reader.h), config.bilateralFilter);
     synchroniseDevices();
     t[2] = clk::now();
-    pipeline.setPose(gt);                                   // ground-truth mode: the pose is given, tracking is skipped
-    const bool tracked = true;
+    bool tracked = true;
+    if (use_tracking && frame > 3) tracked = pipeline.tracking(camera, config.icp_threshold, config.tracking_rate, frame);   // benchmark.cpp:124-125
+    else pipeline.setPose(gt);                              // ground-truth mode (mainQt.cpp:257-265): the pose is given
     t[3] = clk::now();
     const Eigen::Matrix4f pose = pipeline.getPose();
     const float xt = pose(0, 3) - init_pose.x(), yt = pose(1, 3) - init_pose.y(), zt = pose(2, 3) - init_pose.z();

@@ -86,3 +86,41 @@ def box_room(frame: int, dim: float, W: int = 640, H: int = 480, k=DEFAULT_K, n_
                 s = np.where(s > 1e-9, s, np.inf)
                 best = np.minimum(best, s)
     return _finish(best, frame, noise_mm, dropout, seed), pose
+
+
+def look_at_pose(eye, target, roll_rad: float = 0.0) -> np.ndarray:
+    """Camera-to-world pose with +z looking from `eye` to `target`, y roughly down-ish (right-handed)."""
+    eye = np.asarray(eye, np.float64); target = np.asarray(target, np.float64)
+    z = target - eye; z /= np.linalg.norm(z)
+    up = np.array([0.0, 1.0, 0.0])
+    x = np.cross(up, z); x /= np.linalg.norm(x)
+    y = np.cross(z, x)
+    c, s = np.cos(roll_rad), np.sin(roll_rad)
+    x, y = c * x + s * y, -s * x + c * y
+    T = np.eye(4)
+    T[:3, 0], T[:3, 1], T[:3, 2], T[:3, 3] = x, y, z, eye
+    return T.astype(np.float32)
+
+
+def corner_view_pose(frame: int, dim: float) -> np.ndarray:
+    """S3 (tracking tests): the camera looks into a corner of the box room (three mutually perpendicular
+    planes in view, so ICP is well conditioned) while drifting 3 mm and ~0.15 deg per frame."""
+    eye = np.array([0.45, 0.5, 0.42]) * dim + np.array([0.003, -0.002, 0.0025]) * frame
+    target = np.array([0.9, 0.9, 0.9]) * dim + np.array([-0.004, 0.003, 0.0]) * frame
+    return look_at_pose(eye, target, roll_rad=np.deg2rad(0.05 * frame))
+
+
+def corner_view(frame: int, dim: float, W: int = 640, H: int = 480, k=DEFAULT_K, noise_mm: float = 0.0,
+                dropout: float = 0.0, seed: int = 0):
+    """Depth of the box room [0.1, 0.9]*dim^3 from corner_view_pose.  Returns (depth_mm, pose)."""
+    pose = corner_view_pose(frame, dim)
+    dw, t = _rays(W, H, k, pose)
+    lo, hi = 0.1 * dim, 0.9 * dim
+    best = np.full(dw.shape[:2], np.inf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for a in range(3):
+            for plane in (lo, hi):
+                s = (plane - t[a]) / dw[..., a]
+                s = np.where(s > 1e-9, s, np.inf)
+                best = np.minimum(best, s)
+    return _finish(best, frame, noise_mm, dropout, seed), pose

@@ -86,6 +86,13 @@ def load(kind: str = "parity"):
     lib.seo_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p]
     lib.seo_ray_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
     lib.seo_set_counting.argtypes = [C.c_void_p, C.c_int]
+    lib.seo_filter_depth.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.seo_tracking.restype = C.c_int
+    lib.seo_tracking.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]
+    lib.seo_get_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.seo_get_tracking.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.seo_se3_exp.argtypes = [C.c_void_p, C.c_void_p]
+    lib.seo_solve6.argtypes = [C.c_void_p, C.c_void_p]
     lib.seo_reset_counters.argtypes = [C.c_void_p]
     lib.seo_get_counters.argtypes = [C.c_void_p, C.c_void_p]
     lib.seo_set_omp_threads.argtypes = [C.c_int]
@@ -246,6 +253,30 @@ class Oracle:
         tinfo = np.zeros(3, np.float32)
         n = self.lib.seo_ray_blocks(self.h, _ptr(o), _ptr(d), near, far, _ptr(out), max_out, _ptr(tinfo))
         return out[:min(n, max_out)].copy(), tinfo
+
+    # ---- N1 ------------------------------------------------------------------------------
+    def filter_depth(self, filter: bool, levels: int = 3):
+        self.lib.seo_filter_depth(self.h, int(filter), levels)
+
+    def track(self, pose, raycast_pose, k, icp_threshold, iterations):
+        p = np.ascontiguousarray(pose, np.float32).reshape(4, 4).copy()
+        rp = np.ascontiguousarray(raycast_pose, np.float32)
+        kk = np.ascontiguousarray(k, np.float32)
+        it = np.ascontiguousarray(iterations, np.int32)
+        ok = self.lib.seo_tracking(self.h, _ptr(p), _ptr(rp), _ptr(kk), icp_threshold, _ptr(it), len(it))
+        return p, bool(ok)
+
+    def pyramid(self, level):
+        w, h = self.W >> level, self.H >> level
+        d = np.empty((h, w), np.float32); v = np.empty((h, w, 3), np.float32); n = np.empty((h, w, 3), np.float32)
+        self.lib.seo_get_pyramid(self.h, level, _ptr(d), _ptr(v), _ptr(n))
+        return d, v, n
+
+    def tracking_data(self):
+        td = np.empty((self.H, self.W), np.dtype([("result", "<i4"), ("error", "<f4"), ("J", "<f4", (6,))]))
+        red = np.zeros(32, np.float32)
+        self.lib.seo_get_tracking(self.h, _ptr(td), _ptr(red))
+        return td, red
 
     def set_counting(self, on=True):
         self.lib.seo_set_counting(self.h, int(on))
