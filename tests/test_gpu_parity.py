@@ -357,3 +357,48 @@ def test_map_export_import_round_trip(field, mu):
     a.raycast(pose, k, mu); b.raycast(pose, k, mu)
     va, na = a.vertex_normal(); vb, nb = b.vertex_normal()
     assert va.tobytes() == vb.tobytes() and na.tobytes() == nb.tobytes()
+
+
+def test_sdf_ieee_division_fallback_paths(monkeypatch):
+    """The integrate kernel has two instantiations: check-free FMA sequences when every parameter
+    is 0 or within [2^-20, 2^20], plain IEEE operators otherwise.  Both must be bit-exact: (a) forced by the
+    environment, (b) selected automatically by a pose with a 1e-9 rotation entry."""
+    from supereight_b200 import synth
+    dim, mu, W, H = 4.8, 0.1, 160, 120
+    k = scaled_k(W)
+    monkeypatch.setenv("SE_B200_IEEE_DIV", "1")
+    g, o = make_pair(SDF, 256, dim, W, H)
+    pose = run_sequence(g, o, synth.planar_sweep, dim, W, H, k, mu, range(3), noise_mm=2.0)
+    assert_sdf_bit_exact(g, o, pose, k, mu)
+    monkeypatch.delenv("SE_B200_IEEE_DIV")
+    g, o = make_pair(SDF, 256, dim, W, H)
+    for f in range(3):
+        d, pose = synth.planar_sweep(f, dim, W, H, k)
+        pose = pose.copy(); pose[0, 1] = 1e-9; pose[1, 0] = -1e-9      # outside the fast kernel's precondition
+        o.preprocess(d); o.integrate(pose, k, mu, f)
+        g.preprocess(d); g.integrate(pose, k, mu, f)
+    assert_sdf_bit_exact(g, o, pose, k, mu)
+
+
+def test_ragged_image_sizes_and_tiny_volume():
+    """Image sizes that are not multiples of the 8x4 pixel tile, and the smallest supported volume."""
+    from supereight_b200 import synth
+    dim, mu, W, H = 1.0, 0.05, 150, 77
+    k = (110.0, 108.0, 75.0, 38.0)
+    g, o = make_pair(SDF, 16, dim, W, H)
+    for f in range(3):
+        pose = synth.yaw_pose(0.5, 0.5, -0.3, 0.05 * f)
+        d, _ = synth.planar_sweep(0, 1.0, W, H, k, dropout=0.1)      # wall at z = 0.75
+        d = (d.astype(np.float32) * 1.3).astype(np.uint16)           # push it to ~1 m in front of the camera
+        o.preprocess(d); o.integrate(pose, k, mu, f)
+        g.preprocess(d); g.integrate(pose, k, mu, f)
+    assert g.block_count() == o.block_count() and g.block_count() <= 8
+    assert_sdf_bit_exact(g, o, pose, k, mu)
+    g2, o2 = make_pair(OFUSION, 64, 2.0, 33, 17)
+    kk = (30.0, 30.0, 16.0, 8.0)
+    for f in range(2):
+        d, pose = synth.box_room(f, 2.0, 33, 17, kk, n_frames=20)
+        o2.preprocess(d); o2.integrate(pose, kk, 0.02, f)
+        g2.preprocess(d); g2.integrate(pose, kk, 0.02, f)
+    assert np.array_equal(g2.blocks_sorted(False)[0], o2.blocks_sorted(False)[0])
+    assert np.array_equal(g2.nodes_sorted()[0], o2.nodes_sorted()[0])
