@@ -153,6 +153,8 @@ int se_b200_query_rays(se_b200_map* map, const float* origin_dir, int n, float n
 enum { SE_B200_STAGE_PREPROCESS = 0, SE_B200_STAGE_ALLOC = 1, SE_B200_STAGE_FUSE = 2, SE_B200_STAGE_RAYCAST = 3,
        SE_B200_STAGE_RENDER = 4, SE_B200_NUM_STAGES = 5 };
 int se_b200_elapsed_ms(se_b200_map* map, int stage, float* ms);
+/* the per-stage event pairs are recorded by default; 0 turns them off (ten event records less per frame) */
+int se_b200_set_stage_timing(se_b200_map* map, int enable);
 /* counters of the last integrate: [0] nodes, [1] blocks, [2] active blocks, [3] error bits,
  * [4] blocks before the frame, [5] nodes before the frame, [6] octant requests (OFusion) */
 int se_b200_counters(se_b200_map* map, int32_t out[8]);

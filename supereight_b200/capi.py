@@ -24,7 +24,7 @@ EXPORTS = (
     "se_b200_render_track_host", "se_b200_filter_depth", "se_b200_track", "se_b200_download_pyramid",
     "se_b200_download_tracking", "se_b200_block_count", "se_b200_node_count", "se_b200_download_blocks_sorted",
     "se_b200_download_nodes_sorted", "se_b200_upload_blocks", "se_b200_upload_nodes", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
-    "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_counters",
+    "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_set_stage_timing", "se_b200_counters",
     "se_b200_launch_count", "se_b200_device_image",
 )
 
@@ -34,7 +34,8 @@ class SeB200Error(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libse_b200.so")
+    # SE_B200_LIB: load another build of the same library (A/B measurements of kernel variants)
+    return os.environ.get("SE_B200_LIB") or os.path.join(_HERE, "libse_b200.so")
 
 
 def load_library():
@@ -82,6 +83,7 @@ def load_library():
     lib.se_b200_set_voxels.argtypes = [vp, vp, vp, i32]
     lib.se_b200_query_rays.argtypes = [vp, vp, i32, f32, f32, vp, vp]
     lib.se_b200_elapsed_ms.argtypes = [vp, i32, C.POINTER(f32)]
+    lib.se_b200_set_stage_timing.argtypes = [vp, i32]
     lib.se_b200_counters.argtypes = [vp, vp]
     lib.se_b200_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.se_b200_device_image.argtypes = [vp, i32, C.POINTER(vp)]
@@ -309,6 +311,9 @@ class Map:
         idx = STAGES.index(stage) if isinstance(stage, str) else int(stage)
         self._check(self.lib.se_b200_elapsed_ms(self.h, idx, C.byref(ms)))
         return ms.value
+
+    def set_stage_timing(self, enable: bool):
+        self._check(self.lib.se_b200_set_stage_timing(self.h, int(enable)))
 
     def counters(self):
         out = np.zeros(8, np.int32)

@@ -84,6 +84,7 @@ struct se_b200_map {
   long long launches = 0;
   int grid_integrate = 0;
   int parity = 0;
+  bool stage_timing = true;
 
   template <class V> MapView<V> view() const {
     MapView<V> v;
@@ -118,8 +119,8 @@ int check_launch(se_b200_map* m, int n = 1) {
   return SE_B200_OK;
 }
 
-void stage_begin(se_b200_map* m, int s) { cudaEventRecord(m->ev_begin[s], m->stream); }
-void stage_end(se_b200_map* m, int s) { cudaEventRecord(m->ev_end[s], m->stream); m->ev_valid[s] = true; }
+void stage_begin(se_b200_map* m, int s) { if (m->stage_timing) cudaEventRecord(m->ev_begin[s], m->stream); }
+void stage_end(se_b200_map* m, int s) { if (m->stage_timing) { cudaEventRecord(m->ev_end[s], m->stream); m->ev_valid[s] = true; } }
 
 // B-spline table of bfusion/bspline_lookup.cc:36-37, regenerated from the closed form it samples
 // (mapping_impl.hpp:94-106): evaluated in double at t = -3 + 6 i / 999 and rounded to float it
@@ -819,6 +820,13 @@ int se_b200_elapsed_ms(se_b200_map* m, int stage, float* ms) {
   DeviceGuard guard(m->device);
   CUDA_TRY(cudaEventSynchronize(m->ev_end[stage]));
   CUDA_TRY(cudaEventElapsedTime(ms, m->ev_begin[stage], m->ev_end[stage]));
+  return SE_B200_OK;
+}
+
+int se_b200_set_stage_timing(se_b200_map* m, int enable) {
+  REQUIRE_MAP(m);
+  m->stage_timing = enable != 0;
+  if (!m->stage_timing) for (bool& v : m->ev_valid) v = false;
   return SE_B200_OK;
 }
 
