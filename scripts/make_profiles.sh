@@ -12,5 +12,5 @@ for WL in planar_sweep_sdf512 box_room_sdf2048; do
 done
 WL=box_room_ofusion1024
 ncu --set full --clock-control none --import-source on -k regex:"k_raycast|k_alloc_ofusion|k_integrate_ofusion|k_active_list|k_alloc_first" \
-    -s 42 -c 5 -o gpurun_out/${R}_full_${WL} python scripts/profile_frames.py $WL 9 > gpurun_out/${R}_full_${WL}.log 2>&1
+    -s 35 -c 5 -o gpurun_out/${R}_full_${WL} python scripts/profile_frames.py $WL 9 > gpurun_out/${R}_full_${WL}.log 2>&1
 ls -la gpurun_out
