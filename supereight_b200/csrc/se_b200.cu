@@ -46,6 +46,7 @@ struct Pools {
   void* block_data = nullptr;
   int* counters = nullptr;
   int* dir = nullptr;
+  int* ndir = nullptr;
 };
 
 }  // namespace
@@ -96,6 +97,7 @@ struct se_b200_map {
     v.block_data = (V*)p.block_data;
     v.counters = p.counters;
     v.dir = p.dir; v.dir_dim = size / kBlockSide;
+    v.ndir = p.ndir;
     return v;
   }
 };
@@ -165,6 +167,12 @@ int create_pools(se_b200_map* m) {
   if (m->size <= 8192 && !getenv("SE_B200_DISABLE_DIRECTORY")) {
     CUDA_TRY(cudaMalloc(&m->p.dir, g * g * g * sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(m->p.dir, 0xFF, g * g * g * sizeof(int), m->stream));          // kEmpty
+    // node directory for levels 1 .. leaves_level-1: (8^leaves - 8) / 7 cells
+    const size_t ncells = (size_t)(((1ll << (3 * m->leaves_level)) - 8) / 7);
+    if (ncells > 0) {
+      CUDA_TRY(cudaMalloc(&m->p.ndir, ncells * sizeof(int)));
+      CUDA_TRY(cudaMemsetAsync(m->p.ndir, 0xFF, ncells * sizeof(int), m->stream));
+    }
   }
   CUDA_TRY(cudaMemsetAsync(m->p.node_child, 0xFF, nn * 8 * sizeof(int), m->stream));      // kEmpty
   CUDA_TRY(cudaMemsetAsync(m->p.node_code, 0, nn * sizeof(unsigned long long), m->stream));
@@ -452,7 +460,7 @@ int se_b200_destroy(se_b200_map* m) {
   DeviceGuard guard(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->p.node_child); cudaFree(m->p.node_code); cudaFree(m->p.node_side); cudaFree(m->p.node_mask); cudaFree(m->p.node_value);
-  cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir);
+  cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir); cudaFree(m->p.ndir);
   cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
   cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_track);
   for (int i = 0; i < 8; ++i) { cudaFree(m->d_scaled_depth[i]); cudaFree(m->d_in_vertex[i]); cudaFree(m->d_in_normal[i]); }

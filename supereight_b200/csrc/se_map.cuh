@@ -71,7 +71,19 @@ template <class V> struct MapView {
   // leaves, written once when a block is created.  nullptr => fall back to the tree descent.
   int* dir;
   int dir_dim;         // G = size / 8
+  // Node directory: the same idea for the internal levels 1 .. leaves_level-1 (level l is a dense (2^l)^3 grid
+  // at offset (8^l - 8) / 7).  It costs 1/7 of the block directory and lets the multi-level (OFusion)
+  // allocation pass test "does the octant at level l exist" with one load.  nullptr => tree descent.
+  int* ndir;
 };
+
+// index of the level-`level` octant containing voxel (x, y, z) in MapView::ndir
+template <class V>
+SE_HD int node_dir_index(const MapView<V>& m, int x, int y, int z, int level) {
+  const int sh = m.max_level - level;
+  const int off = (int)(((1ll << (3 * level)) - 8) / 7);
+  return off + ((((z >> sh) << level) | (y >> sh)) << level | (x >> sh));
+}
 
 // ---- device accessors -------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -382,6 +394,10 @@ __device__ __forceinline__ int find_or_create(const MapView<V>& m, unsigned long
             int x, y, z;
             morton_decode(prefix, x, y, z);
             atomicExch(m.dir + ((z >> 3) * m.dir_dim + (y >> 3)) * m.dir_dim + (x >> 3), idx);
+          } else if (level < m.leaves_level && m.ndir) {
+            int x, y, z;
+            morton_decode(prefix, x, y, z);
+            atomicExch(m.ndir + node_dir_index(m, x, y, z, level), idx);
           }
           c = idx;
         } else {
