@@ -762,8 +762,8 @@ int se_b200_query_interp(se_b200_map* m, const float* pos, int n, float* out) {
   CUDA_TRY(dx.alloc((size_t)n * 3 * sizeof(float)));
   CUDA_TRY(dout.alloc((size_t)n * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(dx.p, pos, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-  if (m->field == SE_B200_SDF) k_query_interp<SdfVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, (float*)dout.p);
-  else k_query_interp<OfuVoxel><<<(n + 127) / 128, 128, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  if (m->field == SE_B200_SDF) k_query_interp<SdfVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, (float*)dout.p);
+  else k_query_interp<OfuVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, (float*)dout.p);
   if (int r = check_launch(m)) return r;
   CUDA_TRY(cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));

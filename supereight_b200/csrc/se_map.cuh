@@ -177,9 +177,11 @@ __device__ __forceinline__ float get_fine_x(const MapView<V>& m, BlockCache& c, 
 
 // gather_points (interp_gather.hpp:105-237): the 8 corners are grouped by the block they fall
 // in; one fetch per group; a missing block reads empty() in cases 0..6 and initValue() in the
-// all-axes-crossing case 7.
+// all-axes-crossing case 7.  The corners span at most two blocks per axis: the (at most 8, usually 1 or
+// 2) block indices are looked up once into `ids` (a per-thread column of shared memory, shared with the
+// gradient), then every corner is one selector + one load -- straight-line code for all 8 crossing cases.
 template <class V>
-__device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int bx, int by, int bz, float p[8]) {
+__device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int (*ids)[128], int bx, int by, int bz, float p[8]) {
   const unsigned cross = ((unsigned)((bx & 7) == 7) << 2) | ((unsigned)((by & 7) == 7) << 1) | (unsigned)((bz & 7) == 7);
   if (cross == 0u) {
     const int b = fetch_block_cached(m, c, bx, by, bz);
@@ -194,29 +196,35 @@ __device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c
     return;
   }
   const float missing = (cross == 7u) ? FieldTraits<V>::init().x : FieldTraits<V>::empty_x();
-  // one fetch per group of corners sharing a block: groups are the subsets g of the crossing axes
-  for (unsigned g = cross;; g = (g - 1u) & cross) {
-    const int gx = (int)((g >> 2) & 1u), gy = (int)((g >> 1) & 1u), gz = (int)(g & 1u);
-    const int b = fetch_block_cached(m, c, bx + gx, by + gy, bz + gz);
+  const int t = threadIdx.x;
+  const int G = m.size >> 3, Bx = bx >> 3, By = by >> 3, Bz = bz >> 3;
+  const unsigned cx = (cross >> 2) & 1u, cy = (cross >> 1) & 1u, cz = cross & 1u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
-      const unsigned cb = ((unsigned)ox << 2) | ((unsigned)oy << 1) | (unsigned)oz;
-      if ((cb & cross) == g)
-        p[i] = (b < 0) ? missing : load_x(m.block_data + (size_t)b * kBlockVoxels + voxel_offset<V>(bx + ox, by + oy, bz + oz));
+  for (int s = 0; s < 8; ++s) {
+    // block (Bx + s.x, By + s.y, Bz + s.z) is needed only if every stepped axis really crosses
+    if ((unsigned)(s & 1) <= cx && (unsigned)((s >> 1) & 1) <= cy && (unsigned)(s >> 2) <= cz) {
+      const int gx = Bx + (s & 1), gy = By + ((s >> 1) & 1), gz = Bz + (s >> 2);
+      int id = kEmpty;
+      if (((unsigned)gx < (unsigned)G) & ((unsigned)gy < (unsigned)G) & ((unsigned)gz < (unsigned)G)) id = fetch_block(m, gx << 3, gy << 3, gz << 3);
+      ids[s][t] = id;
     }
-    if (g == 0u) break;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
+    const int id = ids[(ox & cx) | ((oy & cy) << 1) | ((oz & cz) << 2)][t];
+    p[i] = (id < 0) ? missing : load_x(m.block_data + (size_t)id * kBlockVoxels + voxel_offset<V>(bx + ox, by + oy, bz + oz));
   }
 }
 
 // Octree::interp (octree.hpp:541-563), pos in voxel units
 template <class V>
-__device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c, V3 pos) {
+__device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 pos) {
   const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
   const float fx = pos.x - flx, fy = pos.y - fly, fz = pos.z - flz;
   const int bx = max((int)flx, 0), by = max((int)fly, 0), bz = max((int)flz, 0);
   float p[8];
-  gather_points(m, c, bx, by, bz, p);
+  gather_points(m, c, ids, bx, by, bz, p);
   return (((p[0] * (1 - fx) + p[1] * fx) * (1 - fy)
          + (p[2] * (1 - fx) + p[3] * fx) * fy) * (1 - fz)
         + ((p[4] * (1 - fx) + p[5] * fx) * (1 - fy)
@@ -321,10 +329,10 @@ __device__ __forceinline__ V vol_get(const MapView<V>& m, BlockCache& c, V3 p) {
   return get_fine(m, c, (int)(inv * p.x), (int)(inv * p.y), (int)(inv * p.z));
 }
 template <class V>
-__device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, V3 p) {
+__device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 p) {
   c.n_interp++;
   const float inv = (float)m.size / m.dim;
-  return interp_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
+  return interp_field(m, c, ids, v3(inv * p.x, inv * p.y, inv * p.z));
 }
 template <class V>
 __device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 p) {
