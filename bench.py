@@ -241,11 +241,28 @@ def run_gpu(args, cfg, rank, world, local_rank):
     # ---------------- value: inputs resident in HBM, device-side outputs ----------------
     m = new_map()
 
+    # The four ABI calls of a frame, bound once with raw pointers (no per-call numpy conversion): the Python
+    # glue would otherwise cost as much as a kernel.
+    import ctypes as C
+    lib = m.lib
+    poses_c = np.ascontiguousarray(poses, np.float32)
+    k_c = np.ascontiguousarray(k, np.float32)
+    pose_ptr = [C.c_void_p(poses_c.ctypes.data + 64 * f) for f in range(n_frames)]
+    k_ptr = C.c_void_p(k_c.ctypes.data)
+    ddepth_ptr = [C.c_void_p(d_depth[f].data_ptr()) for f in range(n_frames)]
+    drgba_ptr = C.c_void_p(d_rgba.data_ptr())
+    c_mu, c_ls = C.c_float(mu), C.c_float(largestep)
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError(lib.se_b200_last_error().decode())
+
     def step_resident(f):
-        m.preprocess_device_ptr(d_depth[f].data_ptr(), W, H)
-        m.integrate(poses[f], k, mu, f)
-        m.raycast(poses[f], k, mu)
-        m.render_volume_device_ptr(d_rgba.data_ptr(), poses[f], k, mu, largestep, False)
+        h = m.h
+        check(lib.se_b200_preprocess_depth_device(h, ddepth_ptr[f], W, H))
+        check(lib.se_b200_integrate(h, pose_ptr[f], k_ptr, c_mu, f))
+        check(lib.se_b200_raycast(h, pose_ptr[f], k_ptr, c_mu))
+        check(lib.se_b200_render_volume_device(h, drgba_ptr, pose_ptr[f], k_ptr, c_mu, c_ls, 0))
 
     for f in range(warmup):
         flush.zero_(); step_resident(f)
@@ -290,11 +307,15 @@ def run_gpu(args, cfg, rank, world, local_rank):
     h_depth = torch.from_numpy(depth.view(np.int16)).pin_memory()
     h_rgba = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
 
+    hdepth_ptr = [C.c_void_p(h_depth[f].data_ptr()) for f in range(n_frames)]
+    hrgba_ptr = C.c_void_p(h_rgba.data_ptr())
+
     def step_host(f):
-        m.preprocess_host_ptr(h_depth[f].data_ptr(), W, H)          # cudaMemcpyAsync H2D + mm2meters
-        m.integrate(poses[f], k, mu, f)
-        m.raycast(poses[f], k, mu)
-        m.render_volume_host_ptr(h_rgba.data_ptr(), poses[f], k, mu, largestep, False)   # D2H + sync
+        h = m.h
+        check(lib.se_b200_preprocess_depth_host(h, hdepth_ptr[f], W, H))          # cudaMemcpyAsync H2D + mm2meters
+        check(lib.se_b200_integrate(h, pose_ptr[f], k_ptr, c_mu, f))
+        check(lib.se_b200_raycast(h, pose_ptr[f], k_ptr, c_mu))
+        check(lib.se_b200_render_volume_host(h, hrgba_ptr, pose_ptr[f], k_ptr, c_mu, c_ls, 0))   # D2H + sync
 
     for f in range(warmup):
         flush.zero_(); step_host(f)
