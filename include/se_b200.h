@@ -51,7 +51,7 @@ int se_b200_bspline_lut(float out[1000]);
  * Replaces se::Octree<FieldType>::init (se_core/include/se/octree.hpp:411-421) and the image
  * members of DenseSLAMSystem (DenseSLAMSystem.cpp:65-126).  The octree lives in device memory
  * as flat index-addressed pools of `max_nodes` nodes and `max_blocks` 8x8x8 VoxelBlocks
- * (0 = pick a default from the volume size).  `size` must be a power of two >= 16, `W`x`H` is
+ * (0 = default: min((size/8)^3, 2^20) blocks, a quarter as many nodes).  `size` must be a power of two >= 16, `W`x`H` is
  * the computation size. */
 int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W, int H,
                    int64_t max_blocks, int64_t max_nodes, int device);

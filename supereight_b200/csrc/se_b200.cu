@@ -418,7 +418,7 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
   m->leaves_level = m->max_level - 3;
   m->voxel_bytes = field_type == SE_B200_SDF ? sizeof(SdfVoxel) : sizeof(OfuVoxel);
   const int64_t grid_blocks = (int64_t)(size / 8) * (size / 8) * (size / 8);
-  if (max_blocks <= 0) max_blocks = std::min<int64_t>(grid_blocks, 1 << 18);
+  if (max_blocks <= 0) max_blocks = std::min<int64_t>(grid_blocks, 1 << 20);      // 4 GiB (SDF) / 8 GiB (OFusion) of payload at most: sized for 180 GB of HBM
   max_blocks = std::min<int64_t>(max_blocks, grid_blocks);
   if (max_nodes <= 0) max_nodes = max_blocks / 4 + 4096;
   if (max_blocks > (1ll << 30) || max_nodes > (1ll << 28)) { delete m; return fail(SE_B200_ERR_ARG, "pool sizes too large"); }

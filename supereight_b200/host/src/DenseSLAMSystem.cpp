@@ -50,9 +50,11 @@ DenseSLAMSystem::DenseSLAMSystem(const Eigen::Vector2i& inputSize, const Eigen::
   raycast_pose_ = initPose;
   iterations_ = pyramid;
   viewPose_ = &pose_;
+  // device and pool sizes are not part of the reference's constructor: environment overrides, library defaults otherwise
   const char* dev = std::getenv("SE_B200_DEVICE");
+  const char* mb = std::getenv("SE_B200_MAX_BLOCKS");
   SE_CHECK(se_b200_create(&map_, kFieldType, volumeResolution.x(), volumeDimensions.x(), inputSize.x(), inputSize.y(),
-                          0, 0, dev ? std::atoi(dev) : 0), "DenseSLAMSystem");
+                          mb ? std::atoll(mb) : 0, 0, dev ? std::atoi(dev) : 0), "DenseSLAMSystem");
   g_last_map = map_;
 }
 
