@@ -109,9 +109,10 @@ int se_b200_render_track_host(se_b200_map* map, uint8_t* out, const int* track_r
  *   depth pyramid; call it after se_b200_preprocess_depth_*.  `levels` = pyramid depth (config.pyramid.size()).
  * se_b200_track = the body of DenseSLAMSystem::tracking (DenseSLAMSystem.cpp:149-188): half-sample pyramid,
  *   depth2vertex / vertex2normal per level (preprocessing.cpp:89-226), then per level `iterations[level]` rounds
- *   of trackKernel + reduceKernel (tracking.cpp:66-300) on the GPU and the 6x6 solve + SE3 exponential
- *   (tracking.cpp:302-318) on the host, against the vertex / normal maps of the last se_b200_raycast taken from
- *   `raycast_pose`; finally checkPoseKernel (:320-336).  pose_io is updated in place (restored when the check
+ *   of trackKernel + reduceKernel (tracking.cpp:66-300) and the 6x6 solve + SE3 exponential of updatePoseKernel
+ *   (tracking.cpp:302-318), all on the GPU with the pose kept in device memory (no host round trip per iteration;
+ *   iterations after a level's convergence return at once), against the vertex / normal maps of the last
+ *   se_b200_raycast taken from `raycast_pose`; finally checkPoseKernel (:320-336) on the host from the 32 sums.  pose_io is updated in place (restored when the check
  *   fails), *tracked = the check's verdict.  se_b200_render_track_host(map, out, NULL, 0) renders its result. */
 int se_b200_filter_depth(se_b200_map* map, int filter, int levels);
 int se_b200_track(se_b200_map* map, float pose_io[16], const float raycast_pose[16], const float k[4], float icp_threshold,
@@ -120,6 +121,20 @@ int se_b200_track(se_b200_map* map, float pose_io[16], const float raycast_pose[
  * (W*H records of 8 x 4 bytes: int result, float error, float J[6]) + the 32 reduced sums of the last iteration */
 int se_b200_download_pyramid(se_b200_map* map, int level, float* depth, float* vertex, float* normal);
 int se_b200_download_tracking(se_b200_map* map, void* track_data, float reduction[32]);
+
+/* ---- N4: DenseSLAMSystem::dump_mesh (DenseSLAMSystem.cpp:302-322) ---------------------
+ * se_b200_extract_mesh = se::algorithms::marching_cube (meshing.hpp:158-208) with dump_mesh's functors (inside = x < 0,
+ *   select = x) over every allocated VoxelBlock, into a library-owned device buffer; *n_triangles = how many it kept.
+ *   Triangles come out in the order of a serial run over the block list sorted by key (the reference's order depends on
+ *   its OpenMP schedule, meshing.hpp:173-203), cells x-outer / z-inner, table order inside a cell.
+ * se_b200_download_mesh copies them out: 9 floats per triangle = vertexes[0..2] (x, y, z) of the reference's Triangle
+ *   (commons.h:166-168), metres in the volume frame.
+ * se_b200_mc_table (host only, no GPU needed): the 256 x 16 case table the kernel uses, -1 terminated rows in the
+ *   reference's edge numbering (meshing.hpp:58-104).  It is generated, not transcribed: same polygons and triangle counts as
+ *   the reference's edge_tables.h, possibly different diagonals inside a polygon (see csrc/se_meshing.cuh). */
+int se_b200_extract_mesh(se_b200_map* map, int64_t* n_triangles);
+int se_b200_download_mesh(se_b200_map* map, float* triangles, int64_t capacity_triangles);
+void se_b200_mc_table(int8_t table[4096]);
 
 /* ---- inspection: what getMap() / Octree::save expose in the reference --------------------
  * (DenseSLAMSystem.h:295-297, octree.hpp:897-915).  Pool order is arbitrary in the reference

@@ -911,6 +911,80 @@ static inline M4 se3_exp(const float x[6]) {
 // ----------------------------------------------------------------------------
 // the pipeline state the hot path touches (DenseSLAMSystem.h:61-93)
 // ----------------------------------------------------------------------------
+// ----------------------------------------------------------------------------
+// N4: se::algorithms::marching_cube (algorithms/meshing.hpp:158-208) with the functors DenseSLAMSystem::dump_mesh passes
+// (DenseSLAMSystem.cpp:302-322: inside = val.x < 0, select = val.x).
+// `table` = 256 rows of 16 edge indices, -1 terminated, in the reference's edge numbering (the role of triTable,
+// algorithms/edge_tables.h; the tests pass a table generated by tests/mc_table_ref.py -- see DESIGN.md "N4" for how it
+// relates to the reference's).  The reference visits the block list under `omp parallel for` and appends under a mutex, so
+// its triangle order is schedule dependent; here blocks are visited serially in ascending key order.
+// Output: 9 floats per triangle (vertexes[0..2], commons.h:166-168).
+// ----------------------------------------------------------------------------
+namespace meshing {
+// compute_intersection, meshing.hpp:46-55: s + (0.0 - v1) * (d - s) / (v2 - v1); the double (0.0 - v1) rounds back to -v1
+template <class F>
+inline V3 compute_intersection(const Octree<F>& vol, const V3i& source, const V3i& dest) {
+  const float voxelSize = vol.dim / vol.size;
+  const V3 s{source.x * voxelSize, source.y * voxelSize, source.z * voxelSize};
+  const V3 d{dest.x * voxelSize, dest.y * voxelSize, dest.z * voxelSize};
+  const float v1 = vol.get_fine(source.x, source.y, source.z).x;
+  const float v2 = vol.get_fine(dest.x, dest.y, dest.z).x;
+  const float a = (float)(0.0 - v1), den = v2 - v1;
+  return V3{s.x + (a * (d.x - s.x)) / den, s.y + (a * (d.y - s.y)) / den, s.z + (a * (d.z - s.z)) / den};
+}
+// interp_vertexes, meshing.hpp:57-91: edge -> (source, dest) corner offsets
+template <class F>
+inline V3 interp_vertexes(const Octree<F>& vol, int x, int y, int z, int edge) {
+  static const int ends[12][6] = {
+      {0, 0, 0, 1, 0, 0}, {1, 0, 0, 1, 0, 1}, {1, 0, 1, 0, 0, 1}, {0, 0, 0, 0, 0, 1},
+      {0, 1, 0, 1, 1, 0}, {1, 1, 0, 1, 1, 1}, {1, 1, 1, 0, 1, 1}, {0, 1, 0, 0, 1, 1},
+      {0, 0, 0, 0, 1, 0}, {1, 0, 0, 1, 1, 0}, {1, 0, 1, 1, 1, 1}, {0, 0, 1, 0, 1, 1}};
+  if (edge < 0 || edge > 11) return V3{0, 0, 0};
+  const int* e = ends[edge];
+  return compute_intersection(vol, V3i{x + e[0], y + e[1], z + e[2]}, V3i{x + e[3], y + e[4], z + e[5]});
+}
+// compute_index, meshing.hpp:120-149 (both gather_points variants read the same voxels: the cached block for interior
+// cells, get_fine for cells on a +face; get_fine alone covers both)
+template <class F>
+inline uint8_t compute_index(const Octree<F>& vol, int x, int y, int z) {
+  static const int off[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 0, 1}, {0, 0, 1}, {0, 1, 0}, {1, 1, 0}, {1, 1, 1}, {0, 1, 1}};   // :93-103
+  F p[8];
+  for (int i = 0; i < 8; ++i) p[i] = vol.get_fine(x + off[i][0], y + off[i][1], z + off[i][2]);
+  for (int i = 0; i < 8; ++i) if (p[i].y == 0.f) return 0;
+  uint8_t index = 0;
+  for (int i = 0; i < 8; ++i) if (p[i].x < 0.f) index |= (uint8_t)(1u << i);
+  return index;
+}
+inline bool check_vertex(const V3& v, float dim) { return v.x <= 0 || v.y <= 0 || v.z <= 0 || v.x > dim || v.y > dim || v.z > dim; }   // :151-153
+}  // namespace meshing
+
+template <class F>
+inline void marching_cube(const Octree<F>& vol, const int8_t* table, std::vector<float>& triangles) {
+  std::vector<int> order(vol.blocks.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return vol.blocks[a].code < vol.blocks[b].code; });
+  const int size = vol.size;
+  const float dim = vol.dim;
+  for (int b : order) {
+    const V3i start = vol.blocks[b].coords;
+    const int tx = std::min(start.x + kBlockSide, size - 1), ty = std::min(start.y + kBlockSide, size - 1), tz = std::min(start.z + kBlockSide, size - 1);
+    for (int x = start.x; x < tx; ++x)
+      for (int y = start.y; y < ty; ++y)
+        for (int z = start.z; z < tz; ++z) {
+          const uint8_t index = meshing::compute_index(vol, x, y, z);
+          const int8_t* edges = table + 16 * index;
+          for (unsigned e = 0; edges[e] != -1 && e < 16; e += 3) {
+            const V3 v1 = meshing::interp_vertexes(vol, x, y, z, edges[e]);
+            const V3 v2 = meshing::interp_vertexes(vol, x, y, z, edges[e + 1]);
+            const V3 v3 = meshing::interp_vertexes(vol, x, y, z, edges[e + 2]);
+            if (meshing::check_vertex(v1, dim) || meshing::check_vertex(v2, dim) || meshing::check_vertex(v3, dim)) continue;
+            const float t[9] = {v1.x, v1.y, v1.z, v2.x, v2.y, v2.z, v3.x, v3.y, v3.z};
+            triangles.insert(triangles.end(), t, t + 9);
+          }
+        }
+  }
+}
+
 template <class F> struct Pipeline {
   int W, H;
   Octree<F> map;

@@ -175,6 +175,14 @@ void seo_get_pyramid(void* h, int level, float* depth, float* vertex, float* nor
     if (normal) std::memcpy(normal, P.input_normal[level].data(), sizeof(V3) * P.input_normal[level].size());
   });
 }
+// N4: marching cubes; returns the triangle count, copies min(count, capacity) triangles (9 floats each)
+long long seo_marching_cube(void* h, const int8_t* table, float* out, long long capacity) {
+  std::vector<float> tri;
+  DISPATCH(h, { marching_cube(P.map, table, tri); });
+  const long long n = (long long)(tri.size() / 9);
+  if (out) std::memcpy(out, tri.data(), sizeof(float) * 9 * (size_t)std::min(n, capacity));
+  return n;
+}
 void seo_get_tracking(void* h, void* track_data /*W*H*32 B*/, float* reduction /*32*/) {
   DISPATCH(h, {
     if (track_data) std::memcpy(track_data, P.tracking_result.data(), sizeof(TrackData) * P.tracking_result.size());

@@ -6,4 +6,4 @@ package is only the ctypes binding that the tests and bench.py use to call the C
 synthetic depth-stream generator.  There is no CPU fallback: loading fails loudly when the
 library is missing, and every call fails when there is no CUDA device.
 """
-from .capi import Map, SE_B200_SDF, SE_B200_OFUSION, lib_path, load_library, SeB200Error  # noqa: F401
+from .capi import Map, SE_B200_SDF, SE_B200_OFUSION, lib_path, load_library, mc_table, SeB200Error  # noqa: F401

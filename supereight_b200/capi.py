@@ -25,7 +25,7 @@ EXPORTS = (
     "se_b200_download_tracking", "se_b200_block_count", "se_b200_node_count", "se_b200_download_blocks_sorted",
     "se_b200_download_nodes_sorted", "se_b200_upload_blocks", "se_b200_upload_nodes", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
     "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_set_stage_timing", "se_b200_counters",
-    "se_b200_launch_count", "se_b200_device_image",
+    "se_b200_launch_count", "se_b200_device_image", "se_b200_extract_mesh", "se_b200_download_mesh", "se_b200_mc_table",
 )
 
 
@@ -70,6 +70,10 @@ def load_library():
     lib.se_b200_track.argtypes = [vp, vp, vp, vp, f32, vp, i32, C.POINTER(i32)]
     lib.se_b200_download_pyramid.argtypes = [vp, i32, vp, vp, vp]
     lib.se_b200_download_tracking.argtypes = [vp, vp, vp]
+    lib.se_b200_extract_mesh.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.se_b200_download_mesh.argtypes = [vp, vp, C.c_int64]
+    lib.se_b200_mc_table.argtypes = [vp]
+    lib.se_b200_mc_table.restype = None
     lib.se_b200_block_count.argtypes = [vp, C.POINTER(i32)]
     lib.se_b200_node_count.argtypes = [vp, C.POINTER(i32)]
     lib.se_b200_download_blocks_sorted.argtypes = [vp, vp, vp, vp, vp]
@@ -231,6 +235,15 @@ class Map:
         self._check(self.lib.se_b200_render_track_host(self.h, _ptr(out), None, 0))
         return out
 
+    # ---- N4: meshing ----------------------------------------------------------------------
+    def mesh(self):
+        """DenseSLAMSystem::dump_mesh's triangle list: (n, 3, 3) float32, vertexes[0..2] of every triangle, metres"""
+        n = C.c_int64()
+        self._check(self.lib.se_b200_extract_mesh(self.h, C.byref(n)))
+        out = np.empty((n.value, 3, 3), np.float32)
+        self._check(self.lib.se_b200_download_mesh(self.h, _ptr(out) if n.value else None, n.value))
+        return out
+
     # ---- inspection -----------------------------------------------------------------------
     def block_count(self):
         n = C.c_int()
@@ -330,3 +343,10 @@ class Map:
         p = C.c_void_p()
         self._check(self.lib.se_b200_device_image(self.h, which, C.byref(p)))
         return p.value
+
+
+def mc_table():
+    """the marching-cubes case table the meshing kernel uses: (256, 16) int8, -1 terminated rows (host only, no GPU)"""
+    t = np.empty((256, 16), np.int8)
+    load_library().se_b200_mc_table(_ptr(t))
+    return t

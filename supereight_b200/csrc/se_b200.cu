@@ -8,6 +8,10 @@
 #include "../../include/se_b200.h"
 #include "se_kernels.cuh"
 #include "se_tracking.cuh"
+#include "se_meshing.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -77,7 +81,12 @@ struct se_b200_map {
   TrackData* d_trackdata = nullptr;
   float* d_partial = nullptr;
   float* d_reduction = nullptr;
-  float* h_reduction = nullptr;          // pinned, 32 floats
+  float* h_reduction = nullptr;          // pinned, 32 floats + the pose (16)
+  IcpState* d_icp = nullptr;
+  // N4 (meshing)
+  int8_t* d_mc_table = nullptr;
+  float* d_mesh = nullptr;               // 9 floats per triangle
+  long long mesh_triangles = 0, mesh_capacity = 0;
   int* h_counters = nullptr;              // pinned
   cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev_begin[SE_B200_NUM_STAGES] = {}, ev_end[SE_B200_NUM_STAGES] = {};
@@ -381,6 +390,59 @@ int check_pool_error(se_b200_map* m) {
 
 }  // namespace
 
+// ---- N4: meshing ----------------------------------------------------------------------------
+template <class V>
+int extract_mesh_impl(se_b200_map* m, int64_t* n_triangles) {
+  if (int r = fetch_counters(m)) return r;
+  const int n = std::min(m->h_counters[kCntBlocks], m->max_blocks);
+  m->mesh_triangles = 0;
+  if (n_triangles) *n_triangles = 0;
+  if (n == 0) return SE_B200_OK;
+  if (!m->d_mc_table) {
+    int8_t table[256 * kMcRow];
+    mc_generate_table(table);
+    CUDA_TRY(cudaMalloc(&m->d_mc_table, sizeof(table)));
+    CUDA_TRY(cudaMemcpyAsync(m->d_mc_table, table, sizeof(table), cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));          // `table` is on the stack
+  }
+  // block ids in ascending key order (the order a serial run over a sorted block list would visit them)
+  Scratch ids_in, ids_out, keys_out, counts, offsets, tmp;
+  CUDA_TRY(ids_in.alloc((size_t)n * sizeof(int)));
+  CUDA_TRY(ids_out.alloc((size_t)n * sizeof(int)));
+  CUDA_TRY(keys_out.alloc((size_t)n * sizeof(unsigned long long)));
+  CUDA_TRY(counts.alloc((size_t)(n + 1) * sizeof(unsigned int)));
+  CUDA_TRY(offsets.alloc((size_t)(n + 1) * sizeof(unsigned long long)));
+  k_iota<<<(n + 255) / 256, 256, 0, m->stream>>>((int*)ids_in.p, n);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)m->p.block_code, (unsigned long long*)keys_out.p,
+                                           (const int*)ids_in.p, (int*)ids_out.p, n, 0, 64, m->stream));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const unsigned int*)counts.p, (unsigned long long*)offsets.p, n + 1, m->stream));
+  CUDA_TRY(tmp.alloc(std::max(sort_bytes, scan_bytes)));
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, sort_bytes, (const unsigned long long*)m->p.block_code, (unsigned long long*)keys_out.p,
+                                           (const int*)ids_in.p, (int*)ids_out.p, n, 0, 64, m->stream));
+  CUDA_TRY(cudaMemsetAsync(counts.p, 0, (size_t)(n + 1) * sizeof(unsigned int), m->stream));
+  k_mesh_blocks<V, false><<<n, kMeshThreads, 0, m->stream>>>(m->view<V>(), (const int*)ids_out.p, m->d_mc_table, nullptr, (unsigned int*)counts.p, nullptr);
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, (const unsigned int*)counts.p, (unsigned long long*)offsets.p, n + 1, m->stream));
+  unsigned long long total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, (unsigned long long*)offsets.p + n, sizeof(total), cudaMemcpyDeviceToHost, m->stream));
+  if (int r = check_launch(m, 2)) return r;
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if ((long long)total > m->mesh_capacity) {
+    cudaFree(m->d_mesh); m->d_mesh = nullptr; m->mesh_capacity = 0;
+    CUDA_TRY(cudaMalloc(&m->d_mesh, (size_t)total * 9 * sizeof(float)));
+    m->mesh_capacity = (long long)total;
+  }
+  if (total) {
+    k_mesh_blocks<V, true><<<n, kMeshThreads, 0, m->stream>>>(m->view<V>(), (const int*)ids_out.p, m->d_mc_table, (const unsigned long long*)offsets.p, nullptr, m->d_mesh);
+    if (int r = check_launch(m, 1)) return r;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+  }
+  m->mesh_triangles = (long long)total;
+  if (n_triangles) *n_triangles = (int64_t)total;
+  return SE_B200_OK;
+}
+
+
 #define FIELD_DISPATCH(m, call_sdf, call_ofu) ((m)->field == SE_B200_SDF ? (call_sdf) : (call_ofu))
 #define REQUIRE_MAP(m) do { if (!(m)) return fail(SE_B200_ERR_ARG, "null map"); } while (0)
 
@@ -464,7 +526,8 @@ int se_b200_destroy(se_b200_map* m) {
   cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
   cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_track);
   for (int i = 0; i < 8; ++i) { cudaFree(m->d_scaled_depth[i]); cudaFree(m->d_in_vertex[i]); cudaFree(m->d_in_normal[i]); }
-  cudaFree(m->d_trackdata); cudaFree(m->d_partial); cudaFree(m->d_reduction);
+  cudaFree(m->d_trackdata); cudaFree(m->d_partial); cudaFree(m->d_reduction); cudaFree(m->d_icp);
+  cudaFree(m->d_mc_table); cudaFree(m->d_mesh);
   if (m->h_reduction) cudaFreeHost(m->h_reduction);
   if (m->h_counters) cudaFreeHost(m->h_counters);
   for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { if (m->ev_begin[i]) cudaEventDestroy(m->ev_begin[i]); if (m->ev_end[i]) cudaEventDestroy(m->ev_end[i]); }
@@ -786,6 +849,27 @@ int se_b200_query_grad(se_b200_map* m, const float* pos, int n, float* out) {
   return SE_B200_OK;
 }
 
+
+// ---- N4: meshing ----------------------------------------------------------------------------
+int se_b200_extract_mesh(se_b200_map* m, int64_t* n_triangles) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  return FIELD_DISPATCH(m, extract_mesh_impl<SdfVoxel>(m, n_triangles), extract_mesh_impl<OfuVoxel>(m, n_triangles));
+}
+
+int se_b200_download_mesh(se_b200_map* m, float* triangles, int64_t capacity) {
+  REQUIRE_MAP(m);
+  if (capacity < m->mesh_triangles) return fail(SE_B200_ERR_ARG, "mesh buffer smaller than the triangle count se_b200_extract_mesh returned");
+  if (m->mesh_triangles == 0) return SE_B200_OK;
+  if (!triangles) return fail(SE_B200_ERR_ARG, "null mesh buffer");
+  DeviceGuard guard(m->device);
+  CUDA_TRY(cudaMemcpyAsync(triangles, m->d_mesh, (size_t)m->mesh_triangles * 9 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+void se_b200_mc_table(int8_t table[4096]) { mc_generate_table(table); }
+
 int se_b200_set_voxels(se_b200_map* m, const int32_t* xyz, const void* voxels, int n) {
   REQUIRE_MAP(m);
   if (n <= 0) return SE_B200_OK;
@@ -893,57 +977,13 @@ int ensure_tracking_buffers(se_b200_map* m, int levels) {
     CUDA_TRY(cudaMemsetAsync(m->d_trackdata, 0, n * sizeof(TrackData), m->stream));
     CUDA_TRY(cudaMalloc(&m->d_partial, ((n + kTrackThreads - 1) / kTrackThreads) * 32 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->d_reduction, 32 * sizeof(float)));
-    CUDA_TRY(cudaMallocHost(&m->h_reduction, 32 * sizeof(float)));
-    std::memset(m->h_reduction, 0, 32 * sizeof(float));
+    CUDA_TRY(cudaMemsetAsync(m->d_reduction, 0, 32 * sizeof(float), m->stream));
+    CUDA_TRY(cudaMalloc(&m->d_icp, sizeof(IcpState)));
+    CUDA_TRY(cudaMallocHost(&m->h_reduction, 48 * sizeof(float)));
+    std::memset(m->h_reduction, 0, 48 * sizeof(float));
   }
   m->levels = std::max(m->levels, levels);
   return SE_B200_OK;
-}
-
-// 6x6 Cholesky solve of (J^T J) x = J^T e; vals = b[6] followed by the upper triangle (tracking.cpp:42-64, Eigen::LLT there)
-bool solve6(const float* vals, float x[6]) {
-  float C[6][6], L[6][6] = {};
-  int k = 6;
-  for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { C[i][j] = vals[k]; C[j][i] = vals[k]; ++k; }
-  for (int j = 0; j < 6; ++j) {
-    float d = C[j][j];
-    for (int t = 0; t < j; ++t) d -= L[j][t] * L[j][t];
-    if (!(d > 0.f)) return false;
-    L[j][j] = std::sqrt(d);
-    for (int i = j + 1; i < 6; ++i) {
-      float v = C[i][j];
-      for (int t = 0; t < j; ++t) v -= L[i][t] * L[j][t];
-      L[i][j] = v / L[j][j];
-    }
-  }
-  float y[6];
-  for (int i = 0; i < 6; ++i) { float v = vals[i]; for (int t = 0; t < i; ++t) v -= L[i][t] * y[t]; y[i] = v / L[i][i]; }
-  for (int i = 5; i >= 0; --i) { float v = y[i]; for (int t = i + 1; t < 6; ++t) v -= L[t][i] * x[t]; x[i] = v / L[i][i]; }
-  return true;
-}
-
-// exp: se(3) -> SE(3), x = (upsilon, omega), Rodrigues + V matrix (Sophus::SE3f::exp at tracking.cpp:310)
-M4 se3_exp(const float x[6]) {
-  const float wx = x[3], wy = x[4], wz = x[5];
-  const float theta2 = wx * wx + wy * wy + wz * wz, theta = std::sqrt(theta2);
-  float A, B, Cc;
-  if (theta < 1e-4f) { A = 1.f - theta2 / 6.f; B = 0.5f - theta2 / 24.f; Cc = 1.f / 6.f - theta2 / 120.f; }
-  else { A = std::sin(theta) / theta; B = (1.f - std::cos(theta)) / theta2; Cc = (theta - std::sin(theta)) / (theta2 * theta); }
-  const float W[3][3] = {{0, -wz, wy}, {wz, 0, -wx}, {-wy, wx, 0}};
-  float W2[3][3];
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { W2[i][j] = 0; for (int t = 0; t < 3; ++t) W2[i][j] += W[i][t] * W[t][j]; }
-  M4 T; for (float& f : T.m) f = 0.f;
-  for (int i = 0; i < 3; ++i) {
-    float tv = 0;
-    for (int j = 0; j < 3; ++j) {
-      const float I = i == j ? 1.f : 0.f;
-      T.m[4 * i + j] = I + A * W[i][j] + B * W2[i][j];
-      tv += (I + B * W[i][j] + Cc * W2[i][j]) * x[j];
-    }
-    T.m[4 * i + 3] = tv;
-  }
-  T.m[15] = 1.f;
-  return T;
 }
 
 dim3 grid2d(int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); }
@@ -985,30 +1025,34 @@ int se_b200_track(se_b200_map* m, float pose_io[16], const float raycast_pose[16
   }
   if (int r = check_launch(m, 3 * levels - 1)) return r;
 
+  // The coarse-to-fine ICP loop (DenseSLAMSystem.cpp:169-186) is enqueued as a whole: the pose lives on the device,
+  // k_icp_update solves and applies each step there and raises `converged` where the reference breaks out of a level
+  // (later iterations of that level then return at once).  One copy back at the end.
   M4 pose = to_m4(pose_io);
   const M4 old_pose = pose;
+  IcpState init;
+  std::memcpy(init.pose, pose.m, sizeof(init.pose));
+  init.converged = 0; init.pad_[0] = init.pad_[1] = init.pad_[2] = 0;
+  CUDA_TRY(cudaMemcpyAsync(m->d_icp, &init, sizeof(init), cudaMemcpyHostToDevice, m->stream));   // pageable source: staged before the call returns
   TrackParams tp;
   tp.view = mul44(camera_matrix(k), rigid_inverse(to_m4(raycast_pose)));          // projectReference, :167
   tp.refW = m->W; tp.refH = m->H; tp.dist_threshold = kDistThreshold; tp.normal_threshold = kNormalThreshold;
+  int launched = 0;
   for (int level = levels - 1; level >= 0; --level) {
     tp.inW = m->W / (1 << level); tp.inH = m->H / (1 << level);
     const int n = tp.inW * tp.inH, ctas = (n + kTrackThreads - 1) / kTrackThreads;
+    if (iterations[level] > 0) CUDA_TRY(cudaMemsetAsync(&m->d_icp->converged, 0, sizeof(int), m->stream));     // a new level starts unconverged
     for (int i = 0; i < iterations[level]; ++i) {
-      tp.Ttrack = pose;
-      k_track<<<ctas, kTrackThreads, 0, m->stream>>>(m->d_trackdata, m->d_in_vertex[level], m->d_in_normal[level], m->d_vertex, m->d_normal, tp, m->d_partial);
-      k_reduce_final<<<1, 256, 0, m->stream>>>(m->d_partial, ctas, m->d_reduction);
-      if (int r = check_launch(m, 2)) return r;
-      CUDA_TRY(cudaMemcpyAsync(m->h_reduction, m->d_reduction, 32 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
-      CUDA_TRY(cudaStreamSynchronize(m->stream));
-      // updatePoseKernel (tracking.cpp:302-318)
-      float x[6];
-      if (!solve6(m->h_reduction + 1, x)) for (float& v : x) v = 0.f;
-      pose = mul44(se3_exp(x), pose);
-      float n2 = 0.f;
-      for (float v : x) n2 += v * v;
-      if (std::sqrt(n2) < icp_threshold) break;
+      k_track<<<ctas, kTrackThreads, 0, m->stream>>>(m->d_trackdata, m->d_in_vertex[level], m->d_in_normal[level], m->d_vertex, m->d_normal, tp, m->d_icp, m->d_partial);
+      k_icp_update<<<1, 256, 0, m->stream>>>(m->d_partial, ctas, m->d_reduction, m->d_icp, icp_threshold);
+      launched += 2;
     }
   }
+  if (int r = check_launch(m, launched)) return r;
+  CUDA_TRY(cudaMemcpyAsync(m->h_reduction, m->d_reduction, 32 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(m->h_reduction + 32, m->d_icp, 16 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  std::memcpy(pose.m, m->h_reduction + 32, sizeof(pose.m));
   // checkPoseKernel (tracking.cpp:320-336)
   const float* v = m->h_reduction;
   bool ok = true;

@@ -5,8 +5,9 @@
 //   k_vertex2normal   vertex2normalKernel<NegY>    preprocessing.cpp:111-159
 //   k_track           trackKernel                  se_denseslam/src/tracking.cpp:226-300
 //   k_reduce_*        reduceKernel / new_reduce    tracking.cpp:66-224
-// The 6x6 solve and the SE3 exponential of updatePoseKernel (tracking.cpp:302-318) and
-// checkPoseKernel (:320-336) run on the host (se_b200.cu), as small as they are.
+// The 6x6 solve and the SE3 exponential of updatePoseKernel (tracking.cpp:302-318) run in the single CTA that
+// finishes the reduction (k_icp_update), so the whole coarse-to-fine loop is enqueued without a host round trip
+// per iteration; only checkPoseKernel (:320-336) is evaluated on the host, from the 32 sums copied back once.
 // The reference sums its 32 reduction values with an OpenMP reduction (order undefined); here the
 // order is fixed (warp tree -> CTA -> one final CTA), so runs are reproducible, and parity with the
 // CPU oracle is to a tolerance (tests/test_gpu_tracking.py), not bit for bit.
@@ -98,7 +99,10 @@ __global__ void __launch_bounds__(256) k_vertex2normal(float* __restrict__ out, 
   o[0] = n.x; o[1] = n.y; o[2] = n.z;
 }
 
-struct TrackParams { M4 Ttrack, view; int inW, inH, refW, refH; float dist_threshold, normal_threshold; };
+struct TrackParams { M4 view; int inW, inH, refW, refH; float dist_threshold, normal_threshold; };
+
+// device-resident ICP state: pose[16] (row-major, updated in place), then flags
+struct IcpState { float pose[16]; int converged; int pad_[3]; };
 
 constexpr int kTrackThreads = 256;
 
@@ -107,8 +111,12 @@ constexpr int kTrackThreads = 256;
 // partial row.  Fixed order: lane tree (shfl_down), then warps in index order.
 __global__ void __launch_bounds__(kTrackThreads) k_track(TrackData* __restrict__ output, const float* __restrict__ inVertex, const float* __restrict__ inNormal,
                                                          const float* __restrict__ refVertex, const float* __restrict__ refNormal, TrackParams p,
-                                                         float* __restrict__ partial /* gridDim.x * 32 */) {
+                                                         const IcpState* __restrict__ st, float* __restrict__ partial /* gridDim.x * 32 */) {
   __shared__ float s_part[kTrackThreads / 32][32];
+  if (st->converged) return;              // updatePoseKernel already returned true at this level: the loop `break`s (DenseSLAMSystem.cpp:182-183)
+  M4 Ttrack;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) Ttrack.m[e] = st->pose[e];
   const int n = p.inW * p.inH;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float s[32];
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackData* __restrict__
     const V3 inN = ld3(inNormal + 3 * (px + py * p.inW));
     if (inN.x == kInvalid) row.result = -1;
     else {
-      const V3 projectedVertex = xform3(p.Ttrack, ld3(inVertex + 3 * (px + py * p.inW)));
+      const V3 projectedVertex = xform3(Ttrack, ld3(inVertex + 3 * (px + py * p.inW)));
       const V3 projectedPos = xform3(p.view, projectedVertex);
       const float ppx = projectedPos.x / projectedPos.z + 0.5f, ppy = projectedPos.y / projectedPos.z + 0.5f;
       if (ppx < 0.f || ppx > (float)(p.refW - 1) || ppy < 0.f || ppy > (float)(p.refH - 1)) row.result = -2;
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackData* __restrict__
         if (referenceNormal.x == kInvalid) row.result = -3;
         else {
           const V3 diff = ld3(refVertex + 3 * (rx + ry * p.refW)) - projectedVertex;
-          const V3 projectedNormal = rot3(p.Ttrack, inN);
+          const V3 projectedNormal = rot3(Ttrack, inN);
           if (norm3(diff) > p.dist_threshold) row.result = -4;
           else if (dot3(projectedNormal, referenceNormal) < p.normal_threshold) row.result = -5;
           else {
@@ -181,15 +189,80 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackData* __restrict__
   }
 }
 
-// second level: one CTA of 32 x 8 threads sums the partial rows in a fixed order
-__global__ void __launch_bounds__(256) k_reduce_final(const float* __restrict__ partial, int rows, float* __restrict__ out /*32*/) {
+// 6x6 Cholesky solve of (J^T J) x = J^T e; vals = b[6] followed by the upper triangle (tracking.cpp:42-64, Eigen::LLT there)
+SE_HD bool solve6(const float* vals, float x[6]) {
+  float C[6][6], L[6][6];
+  for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) L[i][j] = 0.f;
+  int k = 6;
+  for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { C[i][j] = vals[k]; C[j][i] = vals[k]; ++k; }
+  for (int j = 0; j < 6; ++j) {
+    float d = C[j][j];
+    for (int q = 0; q < j; ++q) d -= L[j][q] * L[j][q];
+    if (!(d > 0.f)) return false;
+    L[j][j] = sqrtf(d);
+    for (int i = j + 1; i < 6; ++i) {
+      float v = C[i][j];
+      for (int q = 0; q < j; ++q) v -= L[i][q] * L[j][q];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  float y[6];
+  for (int i = 0; i < 6; ++i) { float v = vals[i]; for (int q = 0; q < i; ++q) v -= L[i][q] * y[q]; y[i] = v / L[i][i]; }
+  for (int i = 5; i >= 0; --i) { float v = y[i]; for (int q = i + 1; q < 6; ++q) v -= L[q][i] * x[q]; x[i] = v / L[i][i]; }
+  return true;
+}
+
+// exp: se(3) -> SE(3), x = (upsilon, omega), Rodrigues + V matrix (Sophus::SE3f::exp at tracking.cpp:310)
+SE_HD M4 se3_exp(const float x[6]) {
+  const float wx = x[3], wy = x[4], wz = x[5];
+  const float theta2 = wx * wx + wy * wy + wz * wz, theta = sqrtf(theta2);
+  float A, B, Cc;
+  if (theta < 1e-4f) { A = 1.f - theta2 / 6.f; B = 0.5f - theta2 / 24.f; Cc = 1.f / 6.f - theta2 / 120.f; }
+  else { A = sinf(theta) / theta; B = (1.f - cosf(theta)) / theta2; Cc = (theta - sinf(theta)) / (theta2 * theta); }
+  const float W[3][3] = {{0.f, -wz, wy}, {wz, 0.f, -wx}, {-wy, wx, 0.f}};
+  float W2[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { W2[i][j] = 0.f; for (int q = 0; q < 3; ++q) W2[i][j] += W[i][q] * W[q][j]; }
+  M4 T;
+  for (int e = 0; e < 16; ++e) T.m[e] = 0.f;
+  for (int i = 0; i < 3; ++i) {
+    float tv = 0.f;
+    for (int j = 0; j < 3; ++j) {
+      const float I = i == j ? 1.f : 0.f;
+      T.m[4 * i + j] = I + A * W[i][j] + B * W2[i][j];
+      tv += (I + B * W[i][j] + Cc * W2[i][j]) * x[j];
+    }
+    T.m[4 * i + 3] = tv;
+  }
+  T.m[15] = 1.f;
+  return T;
+}
+
+// Second level of reduceKernel + updatePoseKernel (tracking.cpp:208-224, 302-318) in one CTA of 32 x 8 threads:
+// the partial rows are summed in a fixed order, then thread 0 solves the 6x6 system, applies exp(x) to the
+// device-resident pose and raises `converged` when |x| < icp_threshold (the reference `break`s the level there).
+__global__ void __launch_bounds__(256) k_icp_update(const float* __restrict__ partial, int rows, float* __restrict__ out /*32*/,
+                                                    IcpState* __restrict__ st, float icp_threshold) {
   __shared__ float s[8][32];
+  __shared__ float r[32];
+  if (st->converged) return;
   const int k = threadIdx.x & 31, g = threadIdx.x >> 5;
   float v = 0.f;
-  for (int r = g; r < rows; r += 8) v += partial[r * 32 + k];
+  for (int row = g; row < rows; row += 8) v += partial[row * 32 + k];
   s[g][k] = v;
   __syncthreads();
-  if (g == 0) { float t = 0.f; for (int j = 0; j < 8; ++j) t += s[j][k]; out[k] = t; }
+  if (g == 0) { float acc = 0.f; for (int j = 0; j < 8; ++j) acc += s[j][k]; out[k] = acc; r[k] = acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x[6];
+    if (!solve6(r + 1, x)) for (int i = 0; i < 6; ++i) x[i] = 0.f;
+    M4 pose;
+    for (int e = 0; e < 16; ++e) pose.m[e] = st->pose[e];
+    pose = mul44(se3_exp(x), pose);
+    for (int e = 0; e < 16; ++e) st->pose[e] = pose.m[e];
+    float n2 = 0.f;
+    for (int i = 0; i < 6; ++i) n2 += x[i] * x[i];
+    if (sqrtf(n2) < icp_threshold) st->converged = 1;
+  }
 }
 
 }  // namespace se_b200

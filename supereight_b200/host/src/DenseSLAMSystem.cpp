@@ -126,8 +126,23 @@ void DenseSLAMSystem::renderDepth(unsigned char* out, const Eigen::Vector2i&) {
 
 void DenseSLAMSystem::dump_volume(const std::string) {}      // empty in the reference too (DenseSLAMSystem.cpp:270-272)
 
+// DenseSLAMSystem.cpp:302-322: marching cubes on the device (se_b200_extract_mesh), then the file writeVtkMesh produces
+// (commons.h:325-391, without point / cell data): one POINTS entry per triangle corner, "3 i i+1 i+2" polygons.
 void DenseSLAMSystem::dump_mesh(const std::string filename) {
-  std::fprintf(stderr, "DenseSLAMSystem::dump_mesh(%s): marching cubes is outside the GPU hot path (SURVEY.md N4)\n", filename.c_str());
+  int64_t n = 0;
+  SE_CHECK(se_b200_extract_mesh(map_, &n), "dump_mesh");
+  std::vector<float> tri((size_t)n * 9);
+  SE_CHECK(se_b200_download_mesh(map_, tri.data(), n), "dump_mesh");
+  std::ofstream f(filename.c_str());
+  f << "# vtk DataFile Version 1.0" << std::endl;
+  f << "vtk mesh generated from KFusion" << std::endl;
+  f << "ASCII" << std::endl;
+  f << "DATASET POLYDATA" << std::endl;
+  f << "POINTS " << n * 3 << " FLOAT" << std::endl;
+  for (int64_t i = 0; i < n * 3; ++i) f << tri[3 * i] << " " << tri[3 * i + 1] << " " << tri[3 * i + 2] << std::endl;
+  f << "POLYGONS " << n << " " << n * 4 << std::endl;
+  for (int64_t i = 0; i < n; ++i) f << "3 " << 3 * i << " " << 3 * i + 1 << " " << 3 * i + 2 << std::endl;
+  f << std::endl;
 }
 
 void DenseSLAMSystem::getMap(std::shared_ptr<se::MapSnapshot>& out) {

@@ -6,7 +6,7 @@
 // se_apps/src/mainQt.cpp:257-265; poses are relative to the initial position, as setPose expects).
 //
 //   se-denseslam-{sdf,ofusion}-b200-benchmark -i scene.raw -g poses.txt [-v 512] [-s 4.8] [-m 0.1] [-c 1]
-//        [-r 1] [-z 1] [-p 0,0,0] [-k fx,fy,cx,cy] [-o log.tsv] [-d dump.bin] [-b map.bin] [-n max_frames] [-t 0|1] [-f 0|1]
+//        [-r 1] [-z 1] [-p 0,0,0] [-k fx,fy,cx,cy] [-o log.tsv] [-d dump.bin] [-b map.bin] [-M mesh.vtk] [-n max_frames] [-t 0|1] [-f 0|1]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
   config.camera = Eigen::Vector4f(481.2f, 480.f, 320.f, 240.f);
   config.pyramid = {10, 5, 4};
   config.integration_rate = 2; config.rendering_rate = 4; config.mu = 0.1f; config.compute_size_ratio = 1;
-  std::string poses_file, dump_file, map_file;
+  std::string poses_file, dump_file, map_file, mesh_file;
   int max_frames = -1;
   bool use_tracking = false;      // -t 1: track with ICP after the first 4 frames instead of reading the pose file
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -77,6 +77,7 @@ int main(int argc, char** argv) {
     else if (a == "-z") config.rendering_rate = std::atoi(v);
     else if (a == "-o") config.log_file = v;
     else if (a == "-d") dump_file = v;
+    else if (a == "-M") mesh_file = v;
     else if (a == "-b") map_file = v;
     else if (a == "-n") max_frames = std::atoi(v);
     else if (a == "-t") use_tracking = std::atoi(v) != 0;
@@ -156,6 +157,7 @@ int main(int argc, char** argv) {
     std::cerr << "map file round trip: " << (same ? "identical" : "DIFFERENT") << " (" << map->block_keys.size() << " blocks, " << map->node_codes.size() << " nodes)" << std::endl;
     if (!same) return 3;
   }
+  if (!mesh_file.empty()) pipeline.dump_mesh(mesh_file);   // what mainQt.cpp:166-169 does with --dump-volume
   if (!dump_file.empty()) {                                 // parity artefact for tests/test_gpu_host_shim.py
     std::shared_ptr<se::MapSnapshot> map;
     pipeline.getMap(map);

@@ -91,6 +91,8 @@ def load(kind: str = "parity"):
     lib.seo_tracking.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]
     lib.seo_get_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.seo_get_tracking.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.seo_marching_cube.restype = C.c_longlong
+    lib.seo_marching_cube.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
     lib.seo_se3_exp.argtypes = [C.c_void_p, C.c_void_p]
     lib.seo_solve6.argtypes = [C.c_void_p, C.c_void_p]
     lib.seo_reset_counters.argtypes = [C.c_void_p]
@@ -271,6 +273,15 @@ class Oracle:
         d = np.empty((h, w), np.float32); v = np.empty((h, w, 3), np.float32); n = np.empty((h, w, 3), np.float32)
         self.lib.seo_get_pyramid(self.h, level, _ptr(d), _ptr(v), _ptr(n))
         return d, v, n
+
+    def marching_cube(self, table):
+        """N4: triangles (n, 3, 3) float32, blocks in key order; `table` = (256, 16) int8 case table"""
+        tab = np.ascontiguousarray(table, np.int8)
+        n = self.lib.seo_marching_cube(self.h, _ptr(tab), None, 0)
+        out = np.empty((n, 3, 3), np.float32)
+        if n:
+            self.lib.seo_marching_cube(self.h, _ptr(tab), _ptr(out), n)
+        return out
 
     def tracking_data(self):
         td = np.empty((self.H, self.W), np.dtype([("result", "<i4"), ("error", "<f4"), ("J", "<f4", (6,))]))

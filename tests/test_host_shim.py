@@ -64,8 +64,9 @@ def test_shim_frame_loop_matches_oracle(tmp_path, field, mu):
     dump = os.path.join(str(tmp_path), "dump.bin")
     log = os.path.join(str(tmp_path), "log.tsv")
     mapfile = os.path.join(str(tmp_path), "test.bin")
+    meshfile = os.path.join(str(tmp_path), "mesh.vtk")
     r = subprocess.run([exe(field), "-i", raw, "-g", poses_path, "-v", str(size), "-s", str(dim), "-m", str(mu), "-r", "2", "-z", "1",
-                        "-k", ",".join(str(v) for v in k), "-o", log, "-d", dump, "-b", mapfile], capture_output=True, text=True)
+                        "-k", ",".join(str(v) for v in k), "-o", log, "-d", dump, "-b", mapfile, "-M", meshfile], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "map file round trip: identical" in r.stderr          # Octree::save format written, loaded into a fresh map, re-exported
     hdr = struct.unpack_from("<ifQ", open(mapfile, "rb").read(16))
@@ -89,7 +90,18 @@ def test_shim_frame_loop_matches_oracle(tmp_path, field, mu):
     assert np.array_equal(gk, keys) and np.array_equal(gc, codes)
     gd = gd.reshape(-1, 512); gv = gv.reshape(-1, 8)
     vert = vert.reshape(H, W, 3); norm = norm.reshape(H, W, 3)
+    # dump_mesh: the file writeVtkMesh writes (commons.h:325-391)
+    vtk = open(meshfile).read().split("\n")
+    assert vtk[:4] == ["# vtk DataFile Version 1.0", "vtk mesh generated from KFusion", "ASCII", "DATASET POLYDATA"]
+    npts = int(vtk[4].split()[1])
+    assert vtk[4] == f"POINTS {npts} FLOAT" and npts % 3 == 0 and vtk[5 + npts] == f"POLYGONS {npts // 3} {npts // 3 * 4}"
+    assert vtk[6 + npts] == "3 0 1 2" and vtk[5 + npts + npts // 3] == f"3 {npts - 3} {npts - 2} {npts - 1}"
+    pts = np.array([ln.split() for ln in vtk[5:5 + npts]], np.float64).reshape(-1, 3, 3)
     if field == "sdf":
+        import mc_table_ref
+        want = o.marching_cube(mc_table_ref.table())
+        assert pts.shape == want.shape and len(want) > 1000
+        np.testing.assert_allclose(pts, want, rtol=2e-5, atol=0)      # operator<< prints 6 significant digits
         assert np.array_equal(gd["x"].view(np.uint32), data["x"].view(np.uint32)) and np.array_equal(gd["y"], data["y"])
         assert np.array_equal(gv["x"].view(np.uint32), values["x"].view(np.uint32))
         assert np.array_equal(vert.view(np.uint32), o.vertex().view(np.uint32))
