@@ -123,6 +123,23 @@ struct DeviceGuard {
 
 M4 to_m4(const float* p) { M4 m; std::memcpy(m.m, p, sizeof(m.m)); return m; }
 
+// Launch on the map's stream with programmatic stream serialisation (see pdl_prologue in se_map.cuh).
+// SE_B200_NO_PDL=1 falls back to plain stream order (A/B measurements).
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SE_B200_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+template <class... KArgs, class... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in check_launch (cudaGetLastError)
+}
+
 int check_launch(se_b200_map* m, int n = 1) {
   m->launches += n;
   cudaError_t e = cudaGetLastError();
@@ -234,11 +251,11 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   const int threads = 256;
   const int grid_px = pixel_tile_blocks(m->W, m->H, threads);
   if (FieldTraits<V>::is_sdf) {
-    k_alloc_sdf<V><<<grid_px, threads, 0, m->stream>>>(view, m->d_depth, ap);
+    launch_pdl(k_alloc_sdf<V>, grid_px, threads, 0, m->stream, view, m->d_depth, ap);
     if (int r = check_launch(m)) return r;
   } else {
-    k_alloc_ofusion<V><<<grid_px, threads, 0, m->stream>>>(view, m->d_depth, ap, m->d_requests, m->max_requests);
-    k_alloc_first_key_chain<V><<<1, 1024, 0, m->stream>>>(view, m->d_requests, m->max_requests);
+    launch_pdl(k_alloc_ofusion<V>, grid_px, threads, 0, m->stream, view, m->d_depth, ap, m->d_requests, m->max_requests);
+    launch_pdl(k_alloc_first_key_chain<V>, 1, 1024, 0, m->stream, view, m->d_requests, m->max_requests);
     if (int r = check_launch(m, 2)) return r;
   }
   stage_end(m, SE_B200_STAGE_ALLOC);
@@ -269,16 +286,16 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
     }
     m->grid_integrate = m->num_sms * occ;
   }
-  k_active_list<V><<<m->num_sms * 2, threads, 0, m->stream>>>(view, fp, m->d_active_list, parity);
+  launch_pdl(k_active_list<V>, m->num_sms * 2, threads, 0, m->stream, view, fp, m->d_active_list, parity);
   if (FieldTraits<V>::is_sdf) {
     // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
     // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
     bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
     for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
-    if (fast) k_integrate_sdf<true><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
-    else k_integrate_sdf<false><<<m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream>>>(m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
+    if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
+    else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
   } else
-    k_integrate_ofusion<<<m->grid_integrate, threads, 0, m->stream>>>(m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity);
+    launch_pdl(k_integrate_ofusion, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity);
   if (int r = check_launch(m, 2)) return r;
   stage_end(m, SE_B200_STAGE_FUSE);
   return SE_B200_OK;
@@ -299,8 +316,8 @@ int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu, un
   const float step = m->dim / (float)m->size;
   const RaycastParams rp = make_raycast_params(m, pose, k, mu, kFarPlane, step * (float)kBlockSide, 1);
   stage_begin(m, SE_B200_STAGE_RAYCAST);
-  if (stats_dev) k_raycast<V, true><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
-  else k_raycast<V, false><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
+  if (stats_dev) launch_pdl(k_raycast<V, true>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
+  else launch_pdl(k_raycast<V, false>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RAYCAST);
   return SE_B200_OK;
@@ -311,8 +328,8 @@ int render_volume_impl(se_b200_map* m, uchar4* out_dev, const float* view_pose, 
   const RaycastParams rp = make_raycast_params(m, view_pose, k, mu, kFarPlane * 2.0f, largestep, 0);   // DenseSLAMSystem.cpp:283-288
   const V3 light = v3(view_pose[3], view_pose[7], view_pose[11]);
   stage_begin(m, SE_B200_STAGE_RENDER);
-  if (reraycast) k_render_volume<V><<<pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream>>>(m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
-  else k_render_shade<<<(m->W * m->H + 255) / 256, 256, 0, m->stream>>>(m->d_vertex, m->d_normal, light, m->W * m->H, out_dev);
+  if (reraycast) launch_pdl(k_render_volume<V>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
+  else launch_pdl(k_render_shade, (m->W * m->H + 255) / 256, 256, 0, m->stream, m->d_vertex, m->d_normal, light, m->W * m->H, out_dev);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RENDER);
   return SE_B200_OK;
@@ -556,7 +573,7 @@ int se_b200_sync(se_b200_map* m) {
 static int preprocess_common(se_b200_map* m, const uint16_t* src_dev, int inW, int inH) {
   const int ratio = inW / m->W;
   dim3 block(32, 8), grid((m->W + 31) / 32, (m->H + 7) / 8);
-  k_mm2meters<<<grid, block, 0, m->stream>>>(m->d_depth, src_dev, m->W, m->H, inW, ratio);
+  launch_pdl(k_mm2meters, grid, block, 0, m->stream, m->d_depth, src_dev, m->W, m->H, inW, ratio);
   return check_launch(m);
 }
 static int check_ratio(se_b200_map* m, int inW, int inH) {
@@ -999,7 +1016,7 @@ int se_b200_filter_depth(se_b200_map* m, int filter, int levels) {
   if (filter) {
     Gauss5 gs;
     for (int i = 0; i < 5; ++i) { const int x = i - 2; gs.g[i] = expf(-(float)(x * x) / (2 * kGaussDelta * kGaussDelta)); }   // DenseSLAMSystem.cpp:111-118
-    k_bilateral<<<grid2d(m->W, m->H), dim3(32, 8), 0, m->stream>>>(m->d_scaled_depth[0], m->d_depth, m->W, m->H, gs);
+    launch_pdl(k_bilateral, grid2d(m->W, m->H), dim3(32, 8), 0, m->stream, m->d_scaled_depth[0], m->d_depth, m->W, m->H, gs);
     if (int r = check_launch(m)) return r;
   } else {
     CUDA_TRY(cudaMemcpyAsync(m->d_scaled_depth[0], m->d_depth, (size_t)m->W * m->H * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
@@ -1016,12 +1033,12 @@ int se_b200_track(se_b200_map* m, float pose_io[16], const float raycast_pose[16
   const dim3 tb(32, 8);
   // pyramid + per-level vertex / normal maps (DenseSLAMSystem.cpp:149-164)
   for (int i = 1; i < levels; ++i)
-    k_half_sample<<<grid2d(m->W >> i, m->H >> i), tb, 0, m->stream>>>(m->d_scaled_depth[i], m->d_scaled_depth[i - 1], m->W >> i, m->H >> i, kEDelta * 3, 1);
+    launch_pdl(k_half_sample, grid2d(m->W >> i, m->H >> i), tb, 0, m->stream, m->d_scaled_depth[i], m->d_scaled_depth[i - 1], m->W >> i, m->H >> i, kEDelta * 3, 1);
   for (int i = 0; i < levels; ++i) {
     const float s = (float)(1 << i);
     const float ks[4] = { k[0] / s, k[1] / s, k[2] / s, k[3] / s };
-    k_depth2vertex<<<grid2d(m->W >> i, m->H >> i), tb, 0, m->stream>>>(m->d_in_vertex[i], m->d_scaled_depth[i], m->W >> i, m->H >> i, inverse_camera_matrix(ks));
-    k_vertex2normal<<<grid2d(m->W >> i, m->H >> i), tb, 0, m->stream>>>(m->d_in_normal[i], m->d_in_vertex[i], m->W >> i, m->H >> i, k[1] < 0 ? 1 : 0);
+    launch_pdl(k_depth2vertex, grid2d(m->W >> i, m->H >> i), tb, 0, m->stream, m->d_in_vertex[i], m->d_scaled_depth[i], m->W >> i, m->H >> i, inverse_camera_matrix(ks));
+    launch_pdl(k_vertex2normal, grid2d(m->W >> i, m->H >> i), tb, 0, m->stream, m->d_in_normal[i], m->d_in_vertex[i], m->W >> i, m->H >> i, k[1] < 0 ? 1 : 0);
   }
   if (int r = check_launch(m, 3 * levels - 1)) return r;
 
@@ -1043,8 +1060,8 @@ int se_b200_track(se_b200_map* m, float pose_io[16], const float raycast_pose[16
     const int n = tp.inW * tp.inH, ctas = (n + kTrackThreads - 1) / kTrackThreads;
     if (iterations[level] > 0) CUDA_TRY(cudaMemsetAsync(&m->d_icp->converged, 0, sizeof(int), m->stream));     // a new level starts unconverged
     for (int i = 0; i < iterations[level]; ++i) {
-      k_track<<<ctas, kTrackThreads, 0, m->stream>>>(m->d_trackdata, m->d_in_vertex[level], m->d_in_normal[level], m->d_vertex, m->d_normal, tp, m->d_icp, m->d_partial);
-      k_icp_update<<<1, 256, 0, m->stream>>>(m->d_partial, ctas, m->d_reduction, m->d_icp, icp_threshold);
+      launch_pdl(k_track, ctas, kTrackThreads, 0, m->stream, m->d_trackdata, m->d_in_vertex[level], m->d_in_normal[level], m->d_vertex, m->d_normal, tp, m->d_icp, m->d_partial);
+      launch_pdl(k_icp_update, 1, 256, 0, m->stream, m->d_partial, ctas, m->d_reduction, m->d_icp, icp_threshold);
       launched += 2;
     }
   }

@@ -28,6 +28,7 @@ constexpr float kGaussDelta = 4.0f;          // :34
 struct Gauss5 { float g[5]; };
 
 __global__ void __launch_bounds__(256) k_bilateral(float* __restrict__ out, const float* __restrict__ in, int W, int H, Gauss5 gs) {
+  pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
   const int pos = x + y * W;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) k_bilateral(float* __restrict__ out, cons
 }
 
 __global__ void __launch_bounds__(256) k_half_sample(float* __restrict__ out, const float* __restrict__ in, int outW, int outH, float e_d, int r) {
+  pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= outW || y >= outH) return;
   const int inW = outW * 2, cx = 2 * x, cy = 2 * y;
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) k_half_sample(float* __restrict__ out, co
 }
 
 __global__ void __launch_bounds__(256) k_depth2vertex(float* __restrict__ vertex, const float* __restrict__ depth, int W, int H, M4 invK) {
+  pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
   const float d = depth[x + y * W];
@@ -84,6 +87,7 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b) { return v3(a.y * b.z - a.z * b
 
 // invalid pixels get only .x = INVALID written, as in the reference (the rest keeps its previous value)
 __global__ void __launch_bounds__(256) k_vertex2normal(float* __restrict__ out, const float* __restrict__ in, int W, int H, int negY) {
+  pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
   float* o = out + 3 * (x + y * W);
@@ -112,6 +116,7 @@ constexpr int kTrackThreads = 256;
 __global__ void __launch_bounds__(kTrackThreads) k_track(TrackData* __restrict__ output, const float* __restrict__ inVertex, const float* __restrict__ inNormal,
                                                          const float* __restrict__ refVertex, const float* __restrict__ refNormal, TrackParams p,
                                                          const IcpState* __restrict__ st, float* __restrict__ partial /* gridDim.x * 32 */) {
+  pdl_prologue();
   __shared__ float s_part[kTrackThreads / 32][32];
   if (st->converged) return;              // updatePoseKernel already returned true at this level: the loop `break`s (DenseSLAMSystem.cpp:182-183)
   M4 Ttrack;
@@ -242,6 +247,7 @@ SE_HD M4 se3_exp(const float x[6]) {
 // device-resident pose and raises `converged` when |x| < icp_threshold (the reference `break`s the level there).
 __global__ void __launch_bounds__(256) k_icp_update(const float* __restrict__ partial, int rows, float* __restrict__ out /*32*/,
                                                     IcpState* __restrict__ st, float icp_threshold) {
+  pdl_prologue();
   __shared__ float s[8][32];
   __shared__ float r[32];
   if (st->converged) return;
