@@ -1160,8 +1160,10 @@ template <class F> struct Pipeline {
     float fraction = 1.f / (1.f + ((float)delta_t / 4.f));
     fraction = std::max(0.5f, fraction);
     data.x = data.x * fraction;
-    // updateLogs (:145-148): unqualified log2 on a float argument resolves to the double overload
-    const float upd = (float)((double)data.x + std::log2((double)(sample / (1.f - sample))));
+    // updateLogs (:145-148): unqualified log2 on a float argument.  perfstats.h includes <math.h>, whose libstdc++ wrapper
+    // brings std::log2's float overload into the global namespace, so this is log2f and a float sum (confirmed by the
+    // reference build in oracle/_ref, which the oracle matches bit for bit with this reading and not with the double one)
+    const float upd = data.x + std::log2(sample / (1.f - sample));
     data.x = std::max(-1000.f, std::min(upd, 1000.f));
     data.y = (double)timestamp;
   }

@@ -6,10 +6,13 @@
   (/root/reference/se_denseslam/src/bfusion/bspline_lookup.cc:37) -- needs /root/reference.
 * seq_*.npz           : inputs (uint16 depth frames, poses, intrinsics) and outputs (sorted block keys,
   voxel payloads, node codes/values, vertex/normal maps, rendered images) of short sequences run through
-  the CPU oracle (oracle/, parity build).  The reference itself cannot be compiled in this environment
-  (Eigen3/Sophus absent), so these are ORACLE outputs: they pin the oracle against regressions and give the
-  GPU tests committed vectors that do not depend on the oracle being rebuilt.  "parity unpinned" above the
-  se_core structural level still applies (see oracle/se_oracle.hpp).
+  THE REFERENCE ITSELF: oracle/_ref/libse_ref_<field>.so is the reference's own DenseSLAMSystem.cpp (and every
+  header it includes) compiled where it lies under /root/reference against the stand-in Eigen / Sophus headers of
+  oracle/ref_standin (the image has neither library; see oracle/Makefile and ref_standin/Eigen/Dense), run
+  single-threaded (its allocate_level races on children_mask_ otherwise).  The script then checks that the oracle
+  (oracle/, parity build) reproduces every array bit for bit before writing the file, so the fixtures pin the
+  oracle to the reference's code, and the GPU tests get committed vectors that need neither to be rebuilt.
+  Without /root/reference (no oracle/_ref) the script refuses to regenerate them.
 """
 import hashlib
 import os
@@ -47,11 +50,28 @@ def lut_checksum():
         f.write(hashlib.sha256(table.tobytes()).hexdigest() + "  float32[1000] of se_denseslam/src/bfusion/bspline_lookup.cc:37 (see make_golden.py)\n")
 
 
+def run_pipeline(o, name, depth, poses, k):
+    field, size, dim, W, H, mu, scene, frames, noise = SEQS[name]
+    for f in range(frames):
+        o.preprocess(depth[f])
+        o.integrate(poses[f], k, mu, f)
+    o.raycast(poses[-1], k, mu)
+    keys, coords, active, data = o.blocks_sorted()
+    codes, side, mask, values = o.nodes_sorted()
+    return dict(
+        block_keys=keys, block_coords=coords, block_active=active, block_x=data["x"], block_y=data["y"],
+        node_codes=codes, node_side=side, node_mask=mask, node_x=values["x"], node_y=values["y"],
+        vertex=o.vertex(), normal=o.normal(),
+        render_reuse=o.render_volume(poses[-1], k, mu, 0.75 * mu, False),
+        render_view=o.render_volume(poses[0], k, mu, 0.75 * mu, True),
+        render_depth=o.render_depth(),
+    )
+
+
 def run_sequence(name):
     field, size, dim, W, H, mu, scene, frames, noise = SEQS[name]
     k = np.array([v * W / 640.0 for v in synth.DEFAULT_K], np.float32)
     gen = synth.planar_sweep if scene == "plane" else synth.box_room
-    o = oracle_lib.Oracle(field, size, dim, W, H)
     depth = np.empty((frames, H, W), np.uint16)
     poses = np.empty((frames, 4, 4), np.float32)
     for f in range(frames):
@@ -59,28 +79,24 @@ def run_sequence(name):
             depth[f], poses[f] = gen(f * 5, dim, W, H, tuple(k), noise_mm=noise, dropout=0.02)
         else:
             depth[f], poses[f] = gen(f * 3, dim, W, H, tuple(k), n_frames=60, noise_mm=noise, dropout=0.02)
-        o.preprocess(depth[f])
-        o.integrate(poses[f], k, mu, f)
-    o.raycast(poses[-1], k, mu)
-    keys, coords, active, data = o.blocks_sorted()
-    codes, side, mask, values = o.nodes_sorted()
-    view = poses[0]
-    out = dict(
-        field=field, size=size, dim=np.float32(dim), W=W, H=H, mu=np.float32(mu), k=k, depth=depth, poses=poses,
-        block_keys=keys, block_coords=coords, block_active=active, block_x=data["x"], block_y=data["y"],
-        node_codes=codes, node_side=side, node_mask=mask, node_x=values["x"], node_y=values["y"],
-        vertex=o.vertex(), normal=o.normal(),
-        render_reuse=o.render_volume(poses[-1], k, mu, 0.75 * mu, False),
-        render_view=o.render_volume(view, k, mu, 0.75 * mu, True),
-        render_depth=o.render_depth(),
-    )
+    ref = oracle_lib.Oracle(field, size, dim, W, H, kind="ref_sdf" if field == oracle_lib.SDF else "ref_ofusion")
+    ref.lib.seo_set_omp_threads(1)
+    out = run_pipeline(ref, name, depth, poses, k)
+    mine = run_pipeline(oracle_lib.Oracle(field, size, dim, W, H), name, depth, poses, k)
+    for key, want in out.items():
+        got = mine[key]
+        same = got.shape == want.shape and (np.array_equal(got.view(np.uint32), want.view(np.uint32)) if want.dtype == np.float32 else np.array_equal(got, want))
+        assert same, f"{name}: the oracle differs from the reference build in {key}"
+    out.update(field=field, size=size, dim=np.float32(dim), W=W, H=H, mu=np.float32(mu), k=k, depth=depth, poses=poses)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print(name, "blocks", len(keys), "nodes", len(codes), "hits", int((out["normal"][..., 0] != -2).sum()),
-          "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+    print(name, "(reference build == oracle) blocks", len(out["block_keys"]), "nodes", len(out["node_codes"]),
+          "hits", int((out["normal"][..., 0] != -2).sum()), "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
 if __name__ == "__main__":
     oracle_lib.build()
     lut_checksum()
+    if not oracle_lib.have_reference_build():
+        sys.exit("oracle/_ref is missing (needs /root/reference): the committed seq_*.npz are kept")
     for n in SEQS:
         run_sequence(n)

@@ -27,77 +27,94 @@ def build():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
+def lib_file(kind: str) -> str:
+    """"parity" / "fast": the oracle (oracle/_build); "ref_sdf", "ref_ofusion" (+ "_fast"): the reference's own sources built
+    against the stand-in Eigen / Sophus headers (oracle/_ref, see oracle/Makefile) behind the same seo_* entry points."""
+    if kind.startswith("ref_"):
+        return os.path.join(ORACLE_DIR, "_ref", f"libse_{kind}.so")
+    return os.path.join(ORACLE_DIR, "_build", f"liboracle_{kind}.so")
+
+
+def have_reference_build() -> bool:
+    return all(os.path.exists(lib_file(k)) for k in ("ref_sdf", "ref_ofusion"))
+
+
+def _set(lib, name, attr, value):
+    if hasattr(lib, name):              # the reference build exports the pipeline-level subset only
+        setattr(getattr(lib, name), attr, value)
+
+
 def load(kind: str = "parity"):
     if kind in _libs:
         return _libs[kind]
-    path = os.path.join(ORACLE_DIR, "_build", f"liboracle_{kind}.so")
+    path = lib_file(kind)
     if not os.path.exists(path):
         build()
     lib = C.CDLL(path)
-    lib.seo_morton_encode.restype = C.c_uint64
-    lib.seo_morton_encode.argtypes = [C.c_int] * 3
-    lib.seo_morton_decode.argtypes = [C.c_uint64, i32p]
-    lib.seo_level_mask.restype = C.c_uint64
-    lib.seo_key_encode.restype = C.c_uint64
-    lib.seo_key_encode.argtypes = [C.c_int] * 5
-    lib.seo_key_descendant.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
-    lib.seo_key_parent.restype = C.c_uint64
-    lib.seo_key_parent.argtypes = [C.c_uint64, C.c_int]
-    lib.seo_key_child_id.argtypes = [C.c_uint64, C.c_int, C.c_int]
-    lib.seo_key_far_corner.argtypes = [C.c_uint64, C.c_int, C.c_int, i32p]
-    lib.seo_key_face_neighbour.argtypes = [C.c_uint64, C.c_uint, C.c_uint, C.c_uint, i32p]
-    lib.seo_key_exterior_neighbours.argtypes = [u64p, C.c_uint64, C.c_int, C.c_int]
-    lib.seo_key_siblings.argtypes = [u64p, C.c_uint64, C.c_int]
-    lib.seo_keys_unique.argtypes = [u64p, C.c_int]
-    lib.seo_keys_filter_ancestors.argtypes = [u64p, C.c_int, C.c_int]
-    lib.seo_keys_unique_multiscale.argtypes = [u64p, C.c_int, C.c_uint]
-    lib.seo_bspline_lut.restype = C.c_float
-    lib.seo_create.restype = C.c_void_p
-    lib.seo_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
-    lib.seo_destroy.argtypes = [C.c_void_p]
-    lib.seo_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-    lib.seo_set_depth.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_get_depth.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_integrate.restype = C.c_uint
-    lib.seo_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint]
-    lib.seo_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
-    lib.seo_render_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int]
-    lib.seo_render_depth.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_render_track.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
-    lib.seo_get_vertex.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_get_normal.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_set_vertex_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.seo_block_count.argtypes = [C.c_void_p]
-    lib.seo_node_count.argtypes = [C.c_void_p]
-    lib.seo_get_blocks_sorted.argtypes = [C.c_void_p] * 5
-    lib.seo_get_nodes_sorted.argtypes = [C.c_void_p] * 5
-    lib.seo_allocate.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-    lib.seo_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
-    lib.seo_fetch_octant.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
-    lib.seo_fetch_octant_code.restype = C.c_uint64
-    lib.seo_fetch_octant_code.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
-    lib.seo_get_fine.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
-    lib.seo_get_coarse.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
-    lib.seo_set_voxel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
-    lib.seo_set_node_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
-    lib.seo_interp.restype = C.c_float
-    lib.seo_interp.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
-    lib.seo_grad.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, f32p]
-    lib.seo_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p]
-    lib.seo_ray_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
-    lib.seo_set_counting.argtypes = [C.c_void_p, C.c_int]
-    lib.seo_filter_depth.argtypes = [C.c_void_p, C.c_int, C.c_int]
-    lib.seo_tracking.restype = C.c_int
-    lib.seo_tracking.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int]
-    lib.seo_get_pyramid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.seo_get_tracking.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.seo_marching_cube.restype = C.c_longlong
-    lib.seo_marching_cube.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
-    lib.seo_se3_exp.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_solve6.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_reset_counters.argtypes = [C.c_void_p]
-    lib.seo_get_counters.argtypes = [C.c_void_p, C.c_void_p]
-    lib.seo_set_omp_threads.argtypes = [C.c_int]
+    _set(lib, "seo_morton_encode", "restype", C.c_uint64)
+    _set(lib, "seo_morton_encode", "argtypes", [C.c_int] * 3)
+    _set(lib, "seo_morton_decode", "argtypes", [C.c_uint64, i32p])
+    _set(lib, "seo_level_mask", "restype", C.c_uint64)
+    _set(lib, "seo_key_encode", "restype", C.c_uint64)
+    _set(lib, "seo_key_encode", "argtypes", [C.c_int] * 5)
+    _set(lib, "seo_key_descendant", "argtypes", [C.c_uint64, C.c_uint64, C.c_int])
+    _set(lib, "seo_key_parent", "restype", C.c_uint64)
+    _set(lib, "seo_key_parent", "argtypes", [C.c_uint64, C.c_int])
+    _set(lib, "seo_key_child_id", "argtypes", [C.c_uint64, C.c_int, C.c_int])
+    _set(lib, "seo_key_far_corner", "argtypes", [C.c_uint64, C.c_int, C.c_int, i32p])
+    _set(lib, "seo_key_face_neighbour", "argtypes", [C.c_uint64, C.c_uint, C.c_uint, C.c_uint, i32p])
+    _set(lib, "seo_key_exterior_neighbours", "argtypes", [u64p, C.c_uint64, C.c_int, C.c_int])
+    _set(lib, "seo_key_siblings", "argtypes", [u64p, C.c_uint64, C.c_int])
+    _set(lib, "seo_keys_unique", "argtypes", [u64p, C.c_int])
+    _set(lib, "seo_keys_filter_ancestors", "argtypes", [u64p, C.c_int, C.c_int])
+    _set(lib, "seo_keys_unique_multiscale", "argtypes", [u64p, C.c_int, C.c_uint])
+    _set(lib, "seo_bspline_lut", "restype", C.c_float)
+    _set(lib, "seo_create", "restype", C.c_void_p)
+    _set(lib, "seo_create", "argtypes", [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int])
+    _set(lib, "seo_destroy", "argtypes", [C.c_void_p])
+    _set(lib, "seo_preprocess", "argtypes", [C.c_void_p, C.c_void_p, C.c_int, C.c_int])
+    _set(lib, "seo_set_depth", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_get_depth", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_integrate", "restype", C.c_uint)
+    _set(lib, "seo_integrate", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint])
+    _set(lib, "seo_raycast", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float])
+    _set(lib, "seo_render_volume", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int])
+    _set(lib, "seo_render_depth", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_render_track", "argtypes", [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int])
+    _set(lib, "seo_get_vertex", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_get_normal", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_set_vertex_normal", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p])
+    _set(lib, "seo_block_count", "argtypes", [C.c_void_p])
+    _set(lib, "seo_node_count", "argtypes", [C.c_void_p])
+    _set(lib, "seo_get_blocks_sorted", "argtypes", [C.c_void_p] * 5)
+    _set(lib, "seo_get_nodes_sorted", "argtypes", [C.c_void_p] * 5)
+    _set(lib, "seo_allocate", "argtypes", [C.c_void_p, C.c_void_p, C.c_int])
+    _set(lib, "seo_fetch", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int])
+    _set(lib, "seo_fetch_octant", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])
+    _set(lib, "seo_fetch_octant_code", "restype", C.c_uint64)
+    _set(lib, "seo_fetch_octant_code", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int])
+    _set(lib, "seo_get_fine", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)])
+    _set(lib, "seo_get_coarse", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)])
+    _set(lib, "seo_set_voxel", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double])
+    _set(lib, "seo_set_node_value", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double])
+    _set(lib, "seo_interp", "restype", C.c_float)
+    _set(lib, "seo_interp", "argtypes", [C.c_void_p, C.c_float, C.c_float, C.c_float])
+    _set(lib, "seo_grad", "argtypes", [C.c_void_p, C.c_float, C.c_float, C.c_float, f32p])
+    _set(lib, "seo_gather", "argtypes", [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p])
+    _set(lib, "seo_ray_blocks", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p])
+    _set(lib, "seo_set_counting", "argtypes", [C.c_void_p, C.c_int])
+    _set(lib, "seo_filter_depth", "argtypes", [C.c_void_p, C.c_int, C.c_int])
+    _set(lib, "seo_tracking", "restype", C.c_int)
+    _set(lib, "seo_tracking", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int])
+    _set(lib, "seo_get_pyramid", "argtypes", [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+    _set(lib, "seo_get_tracking", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p])
+    _set(lib, "seo_marching_cube", "restype", C.c_longlong)
+    _set(lib, "seo_marching_cube", "argtypes", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong])
+    _set(lib, "seo_se3_exp", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_solve6", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_reset_counters", "argtypes", [C.c_void_p])
+    _set(lib, "seo_get_counters", "argtypes", [C.c_void_p, C.c_void_p])
+    _set(lib, "seo_set_omp_threads", "argtypes", [C.c_int])
     _libs[kind] = lib
     return lib
 

@@ -1,0 +1,57 @@
+"""The oracle against THE REFERENCE'S OWN CODE.
+
+oracle/_ref/libse_ref_<field>.so is /root/reference/se_denseslam/src/DenseSLAMSystem.cpp (with everything it includes:
+octree, allocation, projective functor, ray iterator, interpolation, rendering, tracking, meshing), compiled where it lies,
+unmodified, against the stand-in Eigen / Sophus headers in oracle/ref_standin (the image has neither library), behind the
+same seo_* entry points as the oracle (oracle/ref_capi.cpp).  It is built only where /root/reference exists (the
+development container); the built files travel with the repo snapshot.  Every array the pipeline produces must be
+bit-identical between the two; tests/golden/seq_*.npz are written from this build (tests/golden/make_golden.py).
+
+What this pins and what it does not: the oracle's restatement of the reference's ALGORITHM (control flow, indexing,
+formulas, evaluation order as written in the source) is pinned for every stage of the path.  The linear-algebra layer
+underneath is the stand-in, which evaluates sums left to right in plain fp32 and inverts rigid / camera matrices in closed
+form; real Eigen (SIMD kernels, -march=native) and real Sophus (unit-quaternion rotation) differ from that by a few ulp."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+needs_ref = pytest.mark.skipif(not oracle_lib.have_reference_build(), reason="oracle/_ref not built (needs /root/reference)")
+
+EXACT = ["block_keys", "block_coords", "block_active", "block_x", "block_y", "node_codes", "node_side", "node_mask", "node_x", "node_y",
+         "depth", "vertex", "normal", "render_reuse", "render_view", "render_depth", "get", "interp", "grad", "ray_blocks",
+         "track_result", "track_error", "track_J", "reduction", "pose", "tracked", "mesh_vertices_differ"] + \
+        [f"pyramid{lvl}_{nm}" for lvl in range(3) for nm in ("depth", "vertex", "normal")]
+
+
+def compare(field, size, dim, W, H, frames):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "_ref_compare_worker.py"), field, str(size), str(dim), str(W), str(H), str(frames)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@needs_ref
+@pytest.mark.parametrize("field,size,dim,W,H,frames", [("sdf", 256, 4.8, 160, 120, 5), ("ofusion", 256, 4.8, 160, 120, 5), ("sdf", 128, 2.4, 80, 60, 4)])
+def test_oracle_is_bit_identical_to_the_reference_build(field, size, dim, W, H, frames):
+    res = compare(field, size, dim, W, H, frames)
+    assert res["n_blocks"] > 100 and res["hits"] > 1000
+    wrong = {k: res[k] for k in EXACT if res[k] != 0}
+    assert not wrong, wrong
+    # N4: the reference meshes with its own edge_tables.h, the oracle with the generated table: same cells, same vertex set, same
+    # triangle count; the triangulation of 4..7-gons differs
+    assert res["mesh_triangles"][0] == res["mesh_triangles"][1] > 1000
+
+
+@needs_ref
+def test_reference_build_exports_what_the_oracle_binding_uses():
+    for kind in ("ref_sdf", "ref_ofusion"):
+        lib = oracle_lib.load(kind)
+        for name in ("seo_create", "seo_preprocess", "seo_integrate", "seo_raycast", "seo_render_volume", "seo_get_blocks_sorted", "seo_tracking", "seo_marching_cube"):
+            assert hasattr(lib, name), (kind, name)
+        assert oracle_lib.Oracle(1 if kind == "ref_sdf" else 0, 64, 1.0, 8, 8, kind=kind).h.value is None      # the field type is a compile-time choice
