@@ -136,14 +136,19 @@ class ClockSampler:
 # CPU side: the reference algorithm (oracle port, OpenMP) on the host cores
 # ------------------------------------------------------------------------------------------------
 def run_cpu(cfg, depth, poses, k, warmup, steps, budget_s=25.0):
-    """Times the oracle (oracle/_build/liboracle_fast.so: g++ -O3 -march=x86-64-v3 -fopenmp) over the same
-    frames.  The thread count is calibrated (the reference's alloc pass writes block->active from every
-    ray, which scales badly across sockets), the best one is used and reported."""
+    """Times the reference's CPU implementation of the path over the same frames.
+    kind "reference": oracle/_ref/libse_ref_<field>_fast.so -- the reference's own DenseSLAMSystem.cpp compiled where it lies
+    (g++ -O3 -march=x86-64-v3 -fopenmp, its build uses -O3 -march=native) against the stand-in Eigen / Sophus headers
+    (oracle/Makefile); used whenever that build exists.  kind "port": the oracle (oracle/_build/liboracle_fast.so) otherwise.
+    The thread count is calibrated (the reference's alloc pass writes block->active from every ray, which scales badly
+    across sockets), the best one is used and reported."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
-    lib = oracle_lib.load("fast")
+    ref_kind = ("ref_sdf_fast", "ref_ofusion_fast")[cfg["field"]]
+    kind = ref_kind if os.path.exists(oracle_lib.lib_file(ref_kind)) else "fast"
+    lib = oracle_lib.load(kind)
     ncpu = os.cpu_count() or 1
-    o = oracle_lib.Oracle(cfg["field"], cfg["size"], cfg["dim"], cfg["W"], cfg["H"], kind="fast")
+    o = oracle_lib.Oracle(cfg["field"], cfg["size"], cfg["dim"], cfg["W"], cfg["H"], kind=kind)
     mu = cfg["mu"]
 
     def frame(f):
@@ -177,8 +182,9 @@ def run_cpu(cfg, depth, poses, k, warmup, steps, budget_s=25.0):
         frame(f % n_frames); f += 1; done += 1
     dt = time.perf_counter() - t0
     fps = done / dt if dt > 0 else 0.0
-    return dict(value=fps, unit=UNIT, cores=best, kind="port",
-                sample=f"{done} frames of the same stream after warm-up, oracle port with OpenMP ({best} of {ncpu} host threads, best of {cands})",
+    what = "the reference's own sources (oracle/_ref, stand-in Eigen/Sophus)" if kind != "fast" else "oracle port"
+    return dict(value=fps, unit=UNIT, cores=best, kind="reference" if kind != "fast" else "port",
+                sample=f"{done} frames of the same stream after warm-up, {what} with OpenMP ({best} of {ncpu} host threads, best of {cands})",
                 ms_per_step=1e3 * dt / max(done, 1), steps=done)
 
 

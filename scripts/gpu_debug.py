@@ -32,6 +32,11 @@ for f in range(frames):
     print(f"frame {f}: oracle integrate {1e3*(t1-t0):.1f} ms | gpu alloc {g.elapsed_ms('alloc'):.3f} fuse {g.elapsed_ms('fuse'):.3f} ms", g.counters())
     print("  blocks", compare_blocks(g, o))
     print("  nodes ", compare_nodes(g, o))
+    gc_, gs_, gm_, gv_ = g.nodes_sorted(); oc_, os_, om_, ov_ = o.nodes_sorted()
+    if len(gc_) == len(oc_):
+        bad = np.argwhere(gv_["x"].view(np.uint32) != ov_["x"].view(np.uint32))
+        for n_, s_ in bad[:6]:
+            print(f"    node code {int(gc_[n_]):#x} side {int(gs_[n_])} slot {s_}: gpu {float(gv_['x'][n_, s_])!r} oracle {float(ov_['x'][n_, s_])!r} y {float(gv_['y'][n_, s_])!r}")
     t0 = time.time(); o.raycast(pose, k, mu); t1 = time.time()
     g.raycast(pose, k, mu); gv, gn = g.vertex_normal()
     print(f"  raycast oracle {1e3*(t1-t0):.1f} ms gpu {g.elapsed_ms('raycast'):.3f} ms", compare_images(gv, gn, o.vertex(), o.normal()))
