@@ -36,7 +36,7 @@ WORKLOADS = {
     "planar_sweep_sdf512": dict(field=0, size=512, dim=4.8, mu=0.1, scene="plane", W=640, H=480),
     # configs[2]/[3]: selectable for profiling runs, not bench lines
     "box_room_ofusion1024": dict(field=1, size=1024, dim=4.8, mu=0.008, scene="room", W=640, H=480),
-    "box_room_sdf2048": dict(field=0, size=2048, dim=4.096, mu=0.1, scene="room", W=640, H=480, max_blocks=1 << 20),
+    "box_room_sdf2048": dict(field=0, size=2048, dim=4.096, mu=0.1, scene="room", W=640, H=480, max_blocks=1 << 22),   # a full turn of the room at 2048^3 allocates ~3 M blocks (12 GB)
     "planar_sweep_sdf256_small": dict(field=0, size=256, dim=4.8, mu=0.1, scene="plane", W=160, H=120),
 }
 K_CAM = (481.2, 480.0, 320.0, 240.0)

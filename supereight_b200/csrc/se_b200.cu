@@ -140,6 +140,18 @@ void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cu
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in check_launch (cudaGetLastError)
 }
 
+// Device-visible alias of a page-locked host buffer (under unified addressing every cudaHostAlloc / cudaHostRegister'd
+// range is mapped), or nullptr for pageable memory.  The `_host` entry points use it to let the last kernel write the
+// caller's buffer directly over PCIe instead of staging in HBM and issuing a separate copy.  SE_B200_NO_ZEROCOPY=1 turns
+// it off (A/B measurements).  (Reading a pinned INPUT in place was tried and dropped: no measurable gain over the DMA copy.)
+void* mapped_alias(const void* host) {
+  static const bool off = [] { const char* e = std::getenv("SE_B200_NO_ZEROCOPY"); return e && e[0] == '1'; }();
+  if (off) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return a.devicePointer;
+}
 int check_launch(se_b200_map* m, int n = 1) {
   m->launches += n;
   cudaError_t e = cudaGetLastError();
@@ -683,9 +695,13 @@ int se_b200_render_volume_host(se_b200_map* m, uint8_t* out, const float view_po
                                float mu, float largestep, int reraycast) {
   REQUIRE_MAP(m);
   if (!out) return fail(SE_B200_ERR_ARG, "out is null");
-  if (int r = se_b200_render_volume_device(m, (uint8_t*)m->d_rgba, view_pose, k, mu, largestep, reraycast)) return r;
   DeviceGuard guard(m->device);
-  CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)m->W * m->H * 4, cudaMemcpyDeviceToHost, m->stream));
+  if (void* alias = mapped_alias(out)) {            // pinned destination: the shading kernel writes it in place
+    if (int r = se_b200_render_volume_device(m, (uint8_t*)alias, view_pose, k, mu, largestep, reraycast)) return r;
+  } else {
+    if (int r = se_b200_render_volume_device(m, (uint8_t*)m->d_rgba, view_pose, k, mu, largestep, reraycast)) return r;
+    CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)m->W * m->H * 4, cudaMemcpyDeviceToHost, m->stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return SE_B200_OK;
 }

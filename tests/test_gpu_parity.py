@@ -402,3 +402,34 @@ def test_ragged_image_sizes_and_tiny_volume():
         g2.preprocess(d); g2.integrate(pose, kk, 0.02, f)
     assert np.array_equal(g2.blocks_sorted(False)[0], o2.blocks_sorted(False)[0])
     assert np.array_equal(g2.nodes_sorted()[0], o2.nodes_sorted()[0])
+
+
+def test_host_calls_with_pinned_buffers_match_pageable_ones():
+    """se_b200_render_volume_host writes a page-locked destination in place (no staging copy) and
+    se_b200_preprocess_depth_host copies asynchronously from a page-locked source: same bytes as with pageable buffers"""
+    import ctypes as C
+
+    import torch
+    from supereight_b200 import synth
+    dim, mu, W, H = 4.8, 0.1, 160, 120
+    k = scaled_k(W)
+    g, o = make_pair(SDF, 256, dim, W, H)
+    pinned_depth = torch.empty((H, W), dtype=torch.int16).pin_memory()
+    pinned_out = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+    kk = np.ascontiguousarray(k, np.float32)
+    for f in range(4):
+        d, pose = synth.planar_sweep(f, dim, W, H, k, noise_mm=2.0, dropout=0.01)
+        pinned_depth.numpy()[...] = d.view(np.int16)
+        assert g.lib.se_b200_preprocess_depth_host(g.h, C.c_void_p(pinned_depth.data_ptr()), W, H) == 0
+        o.preprocess(d)
+        g.integrate(pose, k, mu, f); o.integrate(pose, k, mu, f)
+    g.raycast(pose, k, mu); o.raycast(pose, k, mu)
+    p = np.ascontiguousarray(pose, np.float32)
+    for reraycast in (0, 1):
+        pinned_out.zero_()
+        rc = g.lib.se_b200_render_volume_host(g.h, C.c_void_p(pinned_out.data_ptr()), C.c_void_p(p.ctypes.data), C.c_void_p(kk.ctypes.data),
+                                              C.c_float(mu), C.c_float(0.75 * mu), reraycast)
+        assert rc == 0
+        want = o.render_volume(pose, k, mu, 0.75 * mu, bool(reraycast))
+        assert np.array_equal(pinned_out.numpy(), want)
+        assert np.array_equal(g.render_volume(pose, k, mu, 0.75 * mu, bool(reraycast)), want)       # pageable destination
