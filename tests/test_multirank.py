@@ -32,6 +32,6 @@ def test_reference_arm_under_multirank_launch():
     assert len(lines) == 1                                      # rank 0 alone prints
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0      # "reference" where oracle/_ref is built
     for key in ("metric", "unit", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "gpu_launches"):
         assert key in d
