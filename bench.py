@@ -289,7 +289,9 @@ def run_gpu(args, cfg, rank, world, local_rank):
     barrier()
     wall = time.perf_counter() - wall0
     gpu_launches = m.launch_count() - launches0
-    total_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = sum(step_ms)
+    median_ms = sorted(step_ms)[len(step_ms) // 2]      # this rank's median step (SURVEY.md 8d asks for median and mean)
     m.close()
 
     m = new_map()
@@ -358,7 +360,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
         frame_ms = sum(kernels[s]["ms"] for s in stages)
         result = {
             "metric": METRIC, "value": round(aggregate_value(world, steps, total_ms_max), 2), "unit": UNIT, "n_gpus": world,
-            "steps": steps, "warmup": warmup, "ms_per_step": round(total_ms_max / steps, 5), "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(total_ms_max / steps, 5), "ms_per_step_median": round(median_ms, 5),
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "field": "SDF" if cfg["field"] == 0 else "OFusion", "volume": f"{cfg['size']}^3 @ {cfg['dim']} m",
                        "image": f"{W}x{H}", "mu": mu, "scene": cfg["scene"], "noise_mm": 2.0, "dropout": 0.01,
