@@ -404,9 +404,9 @@ def main():
     cfg = WORKLOADS[args.workload]
 
     if args.impl == "reference":
-        # The reference's own CPU implementation of the path.  The real supereight cannot be compiled here
-        # (Eigen3/Sophus absent), so this times the line-faithful oracle port with OpenMP on the
-        # host cores.  Rank 0 alone works; the other ranks exit 0.
+        # The reference's own CPU implementation of the path: oracle/_ref (the reference's sources compiled against
+        # stand-in Eigen / Sophus headers) with OpenMP on the host cores; the oracle port only where that
+        # build is absent.  Rank 0 alone works; the other ranks exit 0.
         if rank != 0:
             return
         warmup = max(args.warmup, 3)
