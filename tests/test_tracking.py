@@ -126,6 +126,15 @@ def test_cuda_front_end_matches_oracle():
     far = gt.copy(); far[:3, 3] += 1.5
     est2, ok2 = g.track(far, pose, K, 1e-5, ITER)
     assert not ok2 and np.array_equal(est2, far)
+    # updatePoseKernel returning true ends a level (DenseSLAMSystem.cpp:182-183): with a threshold every update passes, the
+    # 10/5/4 schedule must do exactly one iteration per level -- on the device that is the `converged` flag in HBM
+    e1, ok1 = g.track(start, pose, K, 1.0, ITER)
+    e2, ok2 = g.track(start, pose, K, 1e-9, [1, 1, 1])
+    assert ok1 == ok2 and np.array_equal(e1.view(np.uint32), e2.view(np.uint32))
+    o1, _ = o.track(start, pose, K, 1.0, ITER)
+    o2, _ = o.track(start, pose, K, 1e-9, [1, 1, 1])
+    assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32))
+    np.testing.assert_allclose(e1, o1, rtol=0, atol=2e-4)
 
 
 @pytest.mark.gpu
