@@ -101,6 +101,17 @@ int se_b200_render_volume_host(se_b200_map* map, uint8_t* out, const float view_
 int se_b200_render_volume_device(se_b200_map* map, uint8_t* out_dev, const float view_pose[16], const float k[4],
                                  float mu, float largestep, int reraycast);
 int se_b200_render_depth_host(se_b200_map* map, uint8_t* out);
+
+/* ---- overlapped host I/O (no counterpart in the reference, whose stages are synchronous) ----------------
+ * The same two stages as se_b200_preprocess_depth_host / se_b200_render_volume_host, but the copies run on the map's own
+ * upload / download streams through double-buffered staging in HBM, ordered against the kernel stream by events:
+ * frame N+1's depth upload and frame N's image download overlap the kernels of the frames in between.  Both calls return
+ * without waiting.  depth_mm must stay valid, and out must not be read, until se_b200_sync (which also drains these
+ * streams) -- or, for out, until two further se_b200_render_volume_host_async calls have been issued and a later
+ * synchronising call returned.  Use page-locked host memory (pageable memory makes the copies synchronous). */
+int se_b200_preprocess_depth_host_async(se_b200_map* map, const uint16_t* depth_mm, int inW, int inH);
+int se_b200_render_volume_host_async(se_b200_map* map, uint8_t* out, const float view_pose[16], const float k[4],
+                                     float mu, float largestep, int reraycast);
 int se_b200_render_track_host(se_b200_map* map, uint8_t* out, const int* track_result, int stride_ints);
 
 /* ---- N1: the tracking front-end either side of the hot path ----------------

@@ -26,6 +26,7 @@ EXPORTS = (
     "se_b200_download_nodes_sorted", "se_b200_upload_blocks", "se_b200_upload_nodes", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
     "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_set_stage_timing", "se_b200_counters",
     "se_b200_launch_count", "se_b200_device_image", "se_b200_extract_mesh", "se_b200_download_mesh", "se_b200_mc_table",
+    "se_b200_preprocess_depth_host_async", "se_b200_render_volume_host_async",
 )
 
 
@@ -55,6 +56,7 @@ def load_library():
     lib.se_b200_set_stream.argtypes = [vp, vp]
     lib.se_b200_sync.argtypes = [vp]
     lib.se_b200_preprocess_depth_host.argtypes = [vp, vp, i32, i32]
+    lib.se_b200_preprocess_depth_host_async.argtypes = [vp, vp, i32, i32]
     lib.se_b200_preprocess_depth_device.argtypes = [vp, vp, i32, i32]
     lib.se_b200_set_depth_m_host.argtypes = [vp, vp]
     lib.se_b200_integrate.argtypes = [vp, vp, vp, f32, u32]
@@ -63,6 +65,7 @@ def load_library():
     lib.se_b200_download_vertex_normal.argtypes = [vp, vp, vp]
     lib.se_b200_upload_vertex_normal.argtypes = [vp, vp, vp]
     lib.se_b200_render_volume_host.argtypes = [vp, vp, vp, vp, f32, f32, i32]
+    lib.se_b200_render_volume_host_async.argtypes = [vp, vp, vp, vp, f32, f32, i32]
     lib.se_b200_render_volume_device.argtypes = [vp, vp, vp, vp, f32, f32, i32]
     lib.se_b200_render_depth_host.argtypes = [vp, vp]
     lib.se_b200_render_track_host.argtypes = [vp, vp, vp, i32]

@@ -89,6 +89,18 @@ struct se_b200_map {
   long long mesh_triangles = 0, mesh_capacity = 0;
   int* h_counters = nullptr;              // pinned
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  // overlapped host I/O (se_b200_*_host_async): the copy engines run on their own streams, double-buffered in HBM, tied
+  // to the kernel stream by events, so frame N+1's upload and frame N's download overlap the kernels
+  struct AsyncIo {
+    cudaStream_t up = nullptr, down = nullptr;
+    unsigned short* d_mm[2] = {nullptr, nullptr};
+    size_t mm_capacity[2] = {0, 0};
+    uchar4* d_out[2] = {nullptr, nullptr};
+    cudaEvent_t uploaded[2] = {}, consumed[2] = {}, rendered[2] = {}, downloaded[2] = {};
+    bool consumed_valid[2] = {false, false}, downloaded_valid[2] = {false, false};
+    int up_slot = 0, down_slot = 0;
+    bool ready = false;
+  } aio;
   cudaEvent_t ev_begin[SE_B200_NUM_STAGES] = {}, ev_end[SE_B200_NUM_STAGES] = {};
   bool ev_valid[SE_B200_NUM_STAGES] = {};
   long long launches = 0;
@@ -560,6 +572,14 @@ int se_b200_destroy(se_b200_map* m) {
   if (m->h_reduction) cudaFreeHost(m->h_reduction);
   if (m->h_counters) cudaFreeHost(m->h_counters);
   for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { if (m->ev_begin[i]) cudaEventDestroy(m->ev_begin[i]); if (m->ev_end[i]) cudaEventDestroy(m->ev_end[i]); }
+  if (m->aio.ready) {
+    cudaStreamSynchronize(m->aio.up); cudaStreamSynchronize(m->aio.down);
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(m->aio.d_mm[i]); cudaFree(m->aio.d_out[i]);
+      cudaEventDestroy(m->aio.uploaded[i]); cudaEventDestroy(m->aio.consumed[i]); cudaEventDestroy(m->aio.rendered[i]); cudaEventDestroy(m->aio.downloaded[i]);
+    }
+    cudaStreamDestroy(m->aio.up); cudaStreamDestroy(m->aio.down);
+  }
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   cudaGetLastError();
   delete m;
@@ -579,6 +599,7 @@ int se_b200_sync(se_b200_map* m) {
   REQUIRE_MAP(m);
   DeviceGuard guard(m->device);
   CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (m->aio.ready) { CUDA_TRY(cudaStreamSynchronize(m->aio.up)); CUDA_TRY(cudaStreamSynchronize(m->aio.down)); }
   return SE_B200_OK;
 }
 
@@ -623,6 +644,66 @@ int se_b200_preprocess_depth_device(se_b200_map* m, const uint16_t* depth_mm_dev
   stage_begin(m, SE_B200_STAGE_PREPROCESS);
   if (int r = preprocess_common(m, depth_mm_dev, inW, inH)) return r;
   stage_end(m, SE_B200_STAGE_PREPROCESS);
+  return SE_B200_OK;
+}
+
+static int ensure_async_io(se_b200_map* m) {
+  if (m->aio.ready) return SE_B200_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&m->aio.up, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&m->aio.down, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaMalloc(&m->aio.d_out[i], (size_t)m->W * m->H * sizeof(uchar4)));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->aio.uploaded[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->aio.consumed[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->aio.rendered[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->aio.downloaded[i], cudaEventDisableTiming));
+  }
+  m->aio.ready = true;
+  return SE_B200_OK;
+}
+
+int se_b200_preprocess_depth_host_async(se_b200_map* m, const uint16_t* depth_mm, int inW, int inH) {
+  REQUIRE_MAP(m);
+  if (!depth_mm) return fail(SE_B200_ERR_ARG, "depth_mm is null");
+  if (int r = check_ratio(m, inW, inH)) return r;
+  DeviceGuard guard(m->device);
+  if (int r = ensure_async_io(m)) return r;
+  auto& a = m->aio;
+  const int s = (a.up_slot ^= 1);
+  const size_t bytes = (size_t)inW * inH * sizeof(uint16_t);
+  if (a.mm_capacity[s] < bytes) {
+    CUDA_TRY(cudaStreamSynchronize(m->stream)); CUDA_TRY(cudaStreamSynchronize(a.up));
+    cudaFree(a.d_mm[s]); a.d_mm[s] = nullptr; a.mm_capacity[s] = 0; a.consumed_valid[s] = false;
+    CUDA_TRY(cudaMalloc(&a.d_mm[s], bytes));
+    a.mm_capacity[s] = bytes;
+  }
+  if (a.consumed_valid[s]) CUDA_TRY(cudaStreamWaitEvent(a.up, a.consumed[s], 0));      // the frame two calls ago has read this buffer
+  CUDA_TRY(cudaMemcpyAsync(a.d_mm[s], depth_mm, bytes, cudaMemcpyHostToDevice, a.up));
+  CUDA_TRY(cudaEventRecord(a.uploaded[s], a.up));
+  CUDA_TRY(cudaStreamWaitEvent(m->stream, a.uploaded[s], 0));
+  stage_begin(m, SE_B200_STAGE_PREPROCESS);
+  if (int r = preprocess_common(m, a.d_mm[s], inW, inH)) return r;
+  stage_end(m, SE_B200_STAGE_PREPROCESS);
+  CUDA_TRY(cudaEventRecord(a.consumed[s], m->stream));
+  a.consumed_valid[s] = true;
+  return SE_B200_OK;
+}
+
+int se_b200_render_volume_host_async(se_b200_map* m, uint8_t* out, const float view_pose[16], const float k[4],
+                                     float mu, float largestep, int reraycast) {
+  REQUIRE_MAP(m);
+  if (!out) return fail(SE_B200_ERR_ARG, "out is null");
+  DeviceGuard guard(m->device);
+  if (int r = ensure_async_io(m)) return r;
+  auto& a = m->aio;
+  const int s = (a.down_slot ^= 1);
+  if (a.downloaded_valid[s]) CUDA_TRY(cudaStreamWaitEvent(m->stream, a.downloaded[s], 0));   // the image two calls ago has left this buffer
+  if (int r = se_b200_render_volume_device(m, (uint8_t*)a.d_out[s], view_pose, k, mu, largestep, reraycast)) return r;
+  CUDA_TRY(cudaEventRecord(a.rendered[s], m->stream));
+  CUDA_TRY(cudaStreamWaitEvent(a.down, a.rendered[s], 0));
+  CUDA_TRY(cudaMemcpyAsync(out, a.d_out[s], (size_t)m->W * m->H * 4, cudaMemcpyDeviceToHost, a.down));
+  CUDA_TRY(cudaEventRecord(a.downloaded[s], a.down));
+  a.downloaded_valid[s] = true;
   return SE_B200_OK;
 }
 

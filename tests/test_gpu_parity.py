@@ -433,3 +433,39 @@ def test_host_calls_with_pinned_buffers_match_pageable_ones():
         want = o.render_volume(pose, k, mu, 0.75 * mu, bool(reraycast))
         assert np.array_equal(pinned_out.numpy(), want)
         assert np.array_equal(g.render_volume(pose, k, mu, 0.75 * mu, bool(reraycast)), want)       # pageable destination
+
+
+def test_overlapped_host_io_gives_the_same_frames():
+    """se_b200_preprocess_depth_host_async / se_b200_render_volume_host_async (copy streams, double-buffered staging): issued
+    back to back without synchronising, the map, the last two images and the vertex / normal maps equal the oracle's"""
+    import ctypes as C
+
+    import torch
+    from supereight_b200 import synth
+    dim, mu, W, H, frames = 4.8, 0.1, 160, 120, 7
+    k = scaled_k(W)
+    kk = np.ascontiguousarray(k, np.float32)
+    g, o = make_pair(SDF, 256, dim, W, H)
+    depth = torch.empty((frames, H, W), dtype=torch.int16).pin_memory()
+    outs = [torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    poses, want = [], []
+    for f in range(frames):
+        d, pose = synth.box_room(f * 5, dim, W, H, k, noise_mm=2.0, dropout=0.01)
+        depth[f].numpy()[...] = d.view(np.int16)
+        poses.append(np.ascontiguousarray(pose, np.float32))
+        o.preprocess(d); o.integrate(pose, k, mu, f); o.raycast(pose, k, mu)
+        want.append(o.render_volume(pose, k, mu, 0.75 * mu, False))
+    for f in range(frames):                                     # no synchronisation inside the loop
+        p = C.c_void_p(poses[f].ctypes.data)
+        assert g.lib.se_b200_preprocess_depth_host_async(g.h, C.c_void_p(depth[f].data_ptr()), W, H) == 0
+        assert g.lib.se_b200_integrate(g.h, p, C.c_void_p(kk.ctypes.data), C.c_float(mu), f) == 0
+        assert g.lib.se_b200_raycast(g.h, p, C.c_void_p(kk.ctypes.data), C.c_float(mu)) == 0
+        assert g.lib.se_b200_render_volume_host_async(g.h, C.c_void_p(outs[f & 1].data_ptr()), p, C.c_void_p(kk.ctypes.data),
+                                                      C.c_float(mu), C.c_float(0.75 * mu), 0) == 0
+    g.sync()
+    assert np.array_equal(outs[(frames - 1) & 1].numpy(), want[-1])
+    assert np.array_equal(outs[(frames - 2) & 1].numpy(), want[-2])
+    res = compare_blocks(g, o)
+    assert res["keys_equal"] and res["x_bit_mismatch"] == 0 and res["y_mismatch"] == 0, res
+    gv, gn = g.vertex_normal()
+    assert np.array_equal(gv.view(np.uint32), o.vertex().view(np.uint32)) and np.array_equal(gn.view(np.uint32), o.normal().view(np.uint32))
