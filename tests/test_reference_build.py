@@ -55,3 +55,37 @@ def test_reference_build_exports_what_the_oracle_binding_uses():
         for name in ("seo_create", "seo_preprocess", "seo_integrate", "seo_raycast", "seo_render_volume", "seo_get_blocks_sorted", "seo_tracking", "seo_marching_cube"):
             assert hasattr(lib, name), (kind, name)
         assert oracle_lib.Oracle(1 if kind == "ref_sdf" else 0, 64, 1.0, 8, 8, kind=kind).h.value is None      # the field type is a compile-time choice
+
+
+REF_TESTS = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "tests")
+REF_TEST_NAMES = ["axisaligned", "image", "aabb_collision", "octree_collision", "octree", "ray_iterator", "alloc", "gather", "interpolation", "io",
+                  "unique", "math", "morton", "multiscale"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="oracle/_ref/tests not built (needs /root/reference)")
+@pytest.mark.parametrize("name", REF_TEST_NAMES)
+def test_the_references_own_unit_tests_pass_on_the_standin_build(name, tmp_path):
+    """se_core/test/**/<name>_unittest.cpp, compiled unmodified against oracle/ref_standin (Eigen + gtest stand-ins): the
+    reference's own known-answer tests hold on the build the oracle is compared with (14 files, 56 tests)"""
+    exe = os.path.join(REF_TESTS, name + "_unittest")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))     # io_unittest writes files
+    assert r.returncode == 0, r.stdout[-3000:]
+    lines = r.stdout.strip().splitlines()
+    assert any(ln.startswith("[  PASSED  ]") for ln in lines) and not any(ln.startswith("[  FAILED  ]") for ln in lines)
+
+
+def test_gtest_standin_reports_failures(tmp_path):
+    """the stand-in gtest.h must fail when an assertion fails (fatal ones return, non-fatal ones continue)"""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "gtest/gtest.h"\n'
+                   'TEST(S, ok) { ASSERT_EQ(2, 1 + 1); }\n'
+                   'TEST(S, fatal) { ASSERT_EQ(3, 1 + 1) << "msg"; std::printf("UNREACHED\\n"); }\n'
+                   'TEST(S, nonfatal) { EXPECT_TRUE(false); std::printf("CONTINUED\\n"); }\n')
+    standin = os.path.join(os.path.dirname(HERE), "oracle", "ref_standin")
+    exe = str(tmp_path / "t")
+    subprocess.run(["/usr/bin/g++", "-std=c++14", "-I" + standin, str(src), os.path.join(standin, "gtest", "gtest_main.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "[  PASSED  ] 1 tests." in r.stdout and "[  FAILED  ] 2 tests." in r.stdout
+    assert "UNREACHED" not in r.stdout and "CONTINUED" in r.stdout and "msg" in r.stdout
+
