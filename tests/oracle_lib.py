@@ -24,7 +24,8 @@ u8p = C.POINTER(C.c_uint8)
 
 
 def build():
-    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    """the oracle libraries only; oracle/_ref (minutes of compilation) is built by __graft_entry__.build() / `make -C oracle`"""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def lib_file(kind: str) -> str:
