@@ -403,7 +403,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
                        "parallelism": f"replicas x{world} (one map per GPU)", "l2": "flushed between timed steps (256 MiB write)",
                        "blocks": counters["blocks"], "active_blocks": counters["active"], "nodes": counters["nodes"]},
             "e2e": {"value": round(aggregate_value(world, steps, e2e_ms_max), 2), "unit": UNIT, "h2d_bytes_per_step": W * H * 2,
-                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(e2e_ms_max / steps, 5), "result_checksum": checksum},
+                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(e2e_ms_max / steps, 5), "result_checksum": checksum,
+                    "api": "synchronous se_b200_preprocess_depth_host .. se_b200_render_volume_host per frame (the reference's stage semantics)"},
             "e2e_overlapped": ({"value": round(aggregate_value(world, steps, ov_ms_max), 2), "unit": UNIT, "ms_per_step": round(ov_ms_max / steps, 5),
                                 "api": "se_b200_preprocess_depth_host_async + se_b200_render_volume_host_async (copy streams, double-buffered); "
                                        "same bytes per step as e2e, frames issued back to back, one synchronisation at the end, no L2 flush"}
