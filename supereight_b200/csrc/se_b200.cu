@@ -71,6 +71,7 @@ struct se_b200_map {
   size_t depth_mm_capacity = 0;
   int* d_active_list = nullptr;
   unsigned long long* d_requests = nullptr;
+  float* d_logodds = nullptr;             // OFusion: log-odds increment per (bspline slot(t), slot(t-3)) pair (k_fill_logodds)
   int* d_track = nullptr;
   size_t track_capacity = 0;
   // N1 (tracking front-end): depth pyramid, per-level vertex/normal maps, TrackData, reduction scratch
@@ -306,20 +307,23 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
       CUDA_TRY(cudaFuncSetAttribute(k_integrate_sdf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIntegrateSmem));
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_sdf<true>, kIntegrateWarps * 32, kIntegrateSmem) != cudaSuccess || occ < 1) occ = 2;
     } else {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_ofusion, threads, 0) != cudaSuccess || occ < 1) occ = 2;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_ofusion<true>, threads, 0) != cudaSuccess || occ < 1) occ = 2;
     }
     m->grid_integrate = m->num_sms * occ;
   }
   launch_pdl(k_active_list<V>, m->num_sms * 2, threads, 0, m->stream, view, fp, m->d_active_list, parity);
+  // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
+  // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
+  bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
+  for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
   if (FieldTraits<V>::is_sdf) {
-    // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
-    // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
-    bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
-    for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
     if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
     else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
-  } else
-    launch_pdl(k_integrate_ofusion, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity);
+  } else {
+    static const bool ofusion_fast = [] { const char* e = std::getenv("SE_B200_OFUSION_FAST"); return e && e[0] == '1'; }();
+    if (fast && ofusion_fast && m->d_logodds) launch_pdl(k_integrate_ofusion<true>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity, (const float*)m->d_logodds);
+    else launch_pdl(k_integrate_ofusion<false>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity, (const float*)m->d_logodds);
+  }
   if (int r = check_launch(m, 2)) return r;
   stage_end(m, SE_B200_STAGE_FUSE);
   return SE_B200_OK;
@@ -550,6 +554,10 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
     float lut[1000];
     make_bspline_lut(lut);
     CREATE_TRY(cudaMemcpyToSymbol(c_bspline_lut, lut, sizeof(lut)));
+    const int ncell = kLogOddsDim * kLogOddsDim;
+    CREATE_TRY(cudaMalloc(&m->d_logodds, (size_t)ncell * sizeof(float)));
+    k_fill_logodds<<<(ncell + 255) / 256, 256, 0, m->stream>>>(m->d_logodds);
+    CREATE_TRY(cudaGetLastError());
   }
 #undef CREATE_TRY
   const int r = field_type == SE_B200_SDF ? create_pools<SdfVoxel>(m) : create_pools<OfuVoxel>(m);
@@ -565,7 +573,7 @@ int se_b200_destroy(se_b200_map* m) {
   cudaFree(m->p.node_child); cudaFree(m->p.node_code); cudaFree(m->p.node_side); cudaFree(m->p.node_mask); cudaFree(m->p.node_value);
   cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir); cudaFree(m->p.ndir);
   cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
-  cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_track);
+  cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_logodds); cudaFree(m->d_track);
   for (int i = 0; i < 8; ++i) { cudaFree(m->d_scaled_depth[i]); cudaFree(m->d_in_vertex[i]); cudaFree(m->d_in_normal[i]); }
   cudaFree(m->d_trackdata); cudaFree(m->d_partial); cudaFree(m->d_reduction); cudaFree(m->d_icp);
   cudaFree(m->d_mc_table); cudaFree(m->d_mesh);

@@ -20,6 +20,7 @@
 // interp :541-563 + interpolation/interp_gather.hpp:105-237, grad :652-737).
 #pragma once
 #include "se_math.cuh"
+#include "se_ptx.cuh"
 
 namespace se_b200 {
 
@@ -87,17 +88,6 @@ SE_HD int node_dir_index(const MapView<V>& m, int x, int y, int z, int level) {
 
 // ---- device accessors -------------------------------------------------------------------
 #ifdef __CUDACC__
-
-// Programmatic dependent launch (sm_90+): the per-frame kernels are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs may be scheduled while its predecessor in the
-// stream is still draining.  Every such kernel starts with this: let the NEXT kernel start launching as soon as all of
-// this grid's CTAs are resident, then block until the PREVIOUS grid has completed and its writes are visible.  Nothing is
-// read or written before the wait, so the stream's ordering semantics are unchanged; launched without the attribute both
-// instructions are no-ops.
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
 
 template <class V>
 __device__ __forceinline__ bool in_volume(const MapView<V>& m, int x, int y, int z) {
