@@ -37,8 +37,9 @@ def test_no_device_fails_loudly_not_silently():
 
 
 def test_product_does_not_reference_the_oracle():
-    """Only tests/, bench.py's CPU legs and __graft_entry__.smoke() may touch oracle/."""
-    forbidden = ("oracle_lib", "oracle/", "se_oracle", "liboracle", "seo_")
+    """Only tests/, bench.py's CPU legs and __graft_entry__.smoke() may touch oracle/; the fiber executor of the CPU test
+    tier (tests/simt_emu) is likewise invisible to the package, to bench.py and to the driver's entry points."""
+    forbidden = ("oracle_lib", "oracle/", "se_oracle", "liboracle", "seo_", "simt", "SIMT")
     for dirpath, _, files in os.walk(os.path.join(ROOT, "supereight_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
@@ -46,7 +47,9 @@ def test_product_does_not_reference_the_oracle():
                 for pat in forbidden:
                     assert pat not in text, f"{os.path.join(dirpath, f)} mentions {pat}"
     binary = open(capi.lib_path(), "rb").read()
-    assert b"liboracle" not in binary and b"seo_" not in binary
+    assert b"liboracle" not in binary and b"seo_" not in binary and b"simt" not in binary
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert "simt" not in open(os.path.join(ROOT, f)).read(), f
 
 
 def test_bspline_lut_matches_reference_table_checksum():
