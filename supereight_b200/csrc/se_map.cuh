@@ -115,6 +115,15 @@ __device__ __forceinline__ int fetch_block(const MapView<V>& m, int x, int y, in
   if (m.dir) return __ldg(m.dir + ((z >> 3) * m.dir_dim + (y >> 3)) * m.dir_dim + (x >> 3));
   return fetch_block_tree(m, x, y, z);
 }
+// the same for a BLOCK coordinate (gx, gy, gz) = voxel >> 3, or kEmpty outside the grid: one compare chain, one
+// multiply-add chain, one load (the gather / gradient neighbourhoods are enumerated in block coordinates)
+template <class V>
+__device__ __forceinline__ int fetch_block_cell(const MapView<V>& m, int gx, int gy, int gz) {
+  const unsigned G = (unsigned)m.dir_dim;
+  if (!(((unsigned)gx < G) & ((unsigned)gy < G) & ((unsigned)gz < G))) return kEmpty;
+  if (m.dir) return __ldg(m.dir + (gz * (int)G + gy) * (int)G + gx);
+  return fetch_block_tree(m, gx << 3, gy << 3, gz << 3);
+}
 
 // Octree::fetch_octant (octree.hpp:460-478): node/block at `depth`, is_block tells which pool.
 template <class V>
@@ -178,54 +187,44 @@ __device__ __forceinline__ float get_fine_x(const MapView<V>& m, BlockCache& c, 
 
 // gather_points (interp_gather.hpp:105-237): the 8 corners are grouped by the block they fall
 // in; one fetch per group; a missing block reads empty() in cases 0..6 and initValue() in the
-// all-axes-crossing case 7.  The corners span at most two blocks per axis: the (at most 8, usually 1 or
-// 2) block indices are looked up once into `ids` (a per-thread column of shared memory, shared with the
-// gradient), then every corner is one selector + one load -- straight-line code for all 8 crossing cases.
+// all-axes-crossing case 7.  The corners span at most two blocks per axis.  One straight-line path for
+// all 8 crossing cases (a warp almost always holds both crossing and non-crossing lanes, so a separate
+// fast path would only add its instructions to the slow one): corner s = (ox, oy, oz) lies in block
+// id[s & crossmask]; the eight ids are built with selects, fetching only the blocks whose stepped axes all
+// cross (usually none), and stay in registers.
 template <class V>
-__device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int (*ids)[128], int bx, int by, int bz, float p[8]) {
-  const unsigned cross = ((unsigned)((bx & 7) == 7) << 2) | ((unsigned)((by & 7) == 7) << 1) | (unsigned)((bz & 7) == 7);
-  if (cross == 0u) {
-    const int b = fetch_block_cached(m, c, bx, by, bz);
-    if (b < 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) p[i] = FieldTraits<V>::empty_x();
-    } else {
-      const V* base = m.block_data + (size_t)b * kBlockVoxels + voxel_offset<V>(bx, by, bz);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) p[i] = load_x(base + (i & 1) + ((i & 2) << 2) + ((i & 4) << 4));
-    }
-    return;
-  }
-  const float missing = (cross == 7u) ? FieldTraits<V>::init().x : FieldTraits<V>::empty_x();
-  const int t = threadIdx.x;
-  const int G = m.size >> 3, Bx = bx >> 3, By = by >> 3, Bz = bz >> 3;
-  const unsigned cx = (cross >> 2) & 1u, cy = (cross >> 1) & 1u, cz = cross & 1u;
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    // block (Bx + s.x, By + s.y, Bz + s.z) is needed only if every stepped axis really crosses
-    if ((unsigned)(s & 1) <= cx && (unsigned)((s >> 1) & 1) <= cy && (unsigned)(s >> 2) <= cz) {
-      const int gx = Bx + (s & 1), gy = By + ((s >> 1) & 1), gz = Bz + (s >> 2);
-      int id = kEmpty;
-      if (((unsigned)gx < (unsigned)G) & ((unsigned)gy < (unsigned)G) & ((unsigned)gz < (unsigned)G)) id = fetch_block(m, gx << 3, gy << 3, gz << 3);
-      ids[s][t] = id;
-    }
-  }
+__device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int bx, int by, int bz, float p[8]) {
+  const bool cx = (bx & 7) == 7, cy = (by & 7) == 7, cz = (bz & 7) == 7;
+  const int Bx = bx >> 3, By = by >> 3, Bz = bz >> 3;
+  auto fetch = [&](int ox, int oy, int oz) -> int { return fetch_block_cell(m, Bx + ox, By + oy, Bz + oz); };
+  int id[8];
+  id[0] = fetch_block_cached(m, c, bx, by, bz);
+  id[1] = cx ? fetch(1, 0, 0) : id[0];
+  id[2] = cy ? fetch(0, 1, 0) : id[0];
+  id[3] = cx ? (cy ? fetch(1, 1, 0) : id[1]) : id[2];
+  id[4] = cz ? fetch(0, 0, 1) : id[0];
+  id[5] = cx ? (cz ? fetch(1, 0, 1) : id[1]) : id[4];
+  id[6] = cy ? (cz ? fetch(0, 1, 1) : id[2]) : id[4];
+  id[7] = cx ? (cy ? (cz ? fetch(1, 1, 1) : id[3]) : id[5]) : id[6];
+  const float missing = (cx & cy & cz) ? FieldTraits<V>::init().x : FieldTraits<V>::empty_x();
+  const int xo[2] = { bx & 7, (bx + 1) & 7 };
+  const int yo[2] = { (by & 7) << 3, ((by + 1) & 7) << 3 };
+  const int zo[2] = { (bz & 7) << 6, ((bz + 1) & 7) << 6 };
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int ox = i & 1, oy = (i >> 1) & 1, oz = (i >> 2) & 1;
-    const int id = ids[(ox & cx) | ((oy & cy) << 1) | ((oz & cz) << 2)][t];
-    p[i] = (id < 0) ? missing : load_x(m.block_data + (size_t)id * kBlockVoxels + voxel_offset<V>(bx + ox, by + oy, bz + oz));
+    const int off = xo[i & 1] + yo[(i >> 1) & 1] + zo[(i >> 2) & 1];
+    p[i] = (id[i] < 0) ? missing : load_x(m.block_data + (size_t)id[i] * kBlockVoxels + off);
   }
 }
 
 // Octree::interp (octree.hpp:541-563), pos in voxel units
 template <class V>
-__device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 pos) {
+__device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c, V3 pos) {
   const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
   const float fx = pos.x - flx, fy = pos.y - fly, fz = pos.z - flz;
   const int bx = max((int)flx, 0), by = max((int)fly, 0), bz = max((int)flz, 0);
   float p[8];
-  gather_points(m, c, ids, bx, by, bz, p);
+  gather_points(m, c, bx, by, bz, p);
   return (((p[0] * (1 - fx) + p[1] * fx) * (1 - fy)
          + (p[2] * (1 - fx) + p[3] * fx) * fy) * (1 - fz)
         + ((p[4] * (1 - fx) + p[5] * fx) * (1 - fy)
@@ -268,14 +267,8 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int (*ids)[/*threa
     cz[j] = (unsigned)z4[j] <= (unsigned)hi ? ((((z4[j] >> 3) - Bz) << 18) | ((z4[j] & 7) << 6)) : (1 << 28);
   }
   const int t = threadIdx.x;
-  const int G = m.size >> 3;
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const int gx = Bx + (s & 1), gy = By + ((s >> 1) & 1), gz = Bz + (s >> 2);
-    int id = kEmpty;
-    if (((unsigned)gx < (unsigned)G) & ((unsigned)gy < (unsigned)G) & ((unsigned)gz < (unsigned)G)) id = fetch_block(m, gx << 3, gy << 3, gz << 3);
-    ids[s][t] = id;
-  }
+  for (int s = 0; s < 8; ++s) ids[s][t] = fetch_block_cell(m, Bx + (s & 1), By + ((s >> 1) & 1), Bz + (s >> 2));
   const float initx = FieldTraits<V>::init().x;
 #define S(JX, JY, JZ) ([&]() { const int code = cx[JX] + cy[JY] + cz[JZ]; const int id = ids[(code >> 16) & 7][t]; \
                                return ((code >> 28) != 0 || id < 0) ? initx : load_x(m.block_data + (size_t)id * kBlockVoxels + (code & 0x1ff)); }())
@@ -330,10 +323,10 @@ __device__ __forceinline__ V vol_get(const MapView<V>& m, BlockCache& c, V3 p) {
   return get_fine(m, c, (int)(inv * p.x), (int)(inv * p.y), (int)(inv * p.z));
 }
 template <class V>
-__device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 p) {
+__device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, V3 p) {
   c.n_interp++;
   const float inv = (float)m.size / m.dim;
-  return interp_field(m, c, ids, v3(inv * p.x, inv * p.y, inv * p.z));
+  return interp_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
 }
 template <class V>
 __device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 p) {
