@@ -210,7 +210,7 @@ int create_pools(se_b200_map* m) {
   CUDA_TRY(cudaMalloc(&m->p.block_code, nb * sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&m->p.block_coord, nb * sizeof(int4)));
   CUDA_TRY(cudaMalloc(&m->p.block_active, nb * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&m->p.block_data, nb * kBlockVoxels * sizeof(V)));
+  CUDA_TRY(cudaMalloc(&m->p.block_data, (nb + 1) * kBlockVoxels * sizeof(V)));      // + the never-allocated initValue() payload (se_map.cuh)
   CUDA_TRY(cudaMalloc(&m->p.counters, kNumCounters * sizeof(int)));
   // block directory: (size/8)^3 ints; skipped above 8192^3 (4 GiB) or when SE_B200_DISABLE_DIRECTORY is set
   // (the tree descent is then used everywhere; tests run both ways)
@@ -235,7 +235,7 @@ int create_pools(se_b200_map* m) {
   CUDA_TRY(cudaMemsetAsync(m->p.counters, 0, kNumCounters * sizeof(int), m->stream));
   const int grid = m->num_sms * 8;
   k_fill_voxels<V><<<grid, 256, 0, m->stream>>>((V*)m->p.node_value, nn * 8);
-  k_fill_voxels<V><<<grid, 256, 0, m->stream>>>((V*)m->p.block_data, nb * kBlockVoxels);
+  k_fill_voxels<V><<<grid, 256, 0, m->stream>>>((V*)m->p.block_data, (nb + 1) * kBlockVoxels);
   if (int r = check_launch(m, 2)) return r;
   // root: Octree::init (octree.hpp:411-421): node 0, code 0, side = size
   const int one = 1;

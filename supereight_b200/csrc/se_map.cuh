@@ -49,6 +49,7 @@ template <> struct FieldTraits<OfuVoxel> {
   SE_HD static OfuVoxel init() { OfuVoxel v; v.x = 0.f; v.pad_ = 0.f; v.y = 0.0; return v; }
   SE_HD static float empty_x() { return 0.f; }
 };
+// NB: for both field types empty().x == initValue().x (1 for the TSDF, 0 for the log-odds); gather_points relies on it.
 
 template <class V> struct MapView {
   int size;            // voxels per side
@@ -64,7 +65,7 @@ template <class V> struct MapView {
   unsigned long long* block_code;
   int4* block_coord;   // x, y, z, unused
   int* block_active;
-  V* block_data;
+  V* block_data;       // max_blocks + 1 payloads: the last one is never allocated and always holds initValue() (reads of unallocated blocks go there)
   int* counters;
   // Block directory: dense (size/8)^3 grid of block indices (kEmpty where nothing is allocated),
   // cell = bx + G (by + G bz).  It turns Octree::fetch into one load.  The octree nodes stay the
@@ -196,9 +197,10 @@ template <class V>
 __device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int bx, int by, int bz, float p[8]) {
   const bool cx = (bx & 7) == 7, cy = (by & 7) == 7, cz = (bz & 7) == 7;
   const int Bx = bx >> 3, By = by >> 3, Bz = bz >> 3;
-  auto fetch = [&](int ox, int oy, int oz) -> int { return fetch_block_cell(m, Bx + ox, By + oy, Bz + oz); };
+  auto present = [&](int b) -> int { return b < 0 ? m.max_blocks : b; };      // unallocated -> the initValue() payload
+  auto fetch = [&](int ox, int oy, int oz) -> int { return present(fetch_block_cell(m, Bx + ox, By + oy, Bz + oz)); };
   int id[8];
-  id[0] = fetch_block_cached(m, c, bx, by, bz);
+  id[0] = present(fetch_block_cached(m, c, bx, by, bz));
   id[1] = cx ? fetch(1, 0, 0) : id[0];
   id[2] = cy ? fetch(0, 1, 0) : id[0];
   id[3] = cx ? (cy ? fetch(1, 1, 0) : id[1]) : id[2];
@@ -206,14 +208,15 @@ __device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c
   id[5] = cx ? (cz ? fetch(1, 0, 1) : id[1]) : id[4];
   id[6] = cy ? (cz ? fetch(0, 1, 1) : id[2]) : id[4];
   id[7] = cx ? (cy ? (cz ? fetch(1, 1, 1) : id[3]) : id[5]) : id[6];
-  const float missing = (cx & cy & cz) ? FieldTraits<V>::init().x : FieldTraits<V>::empty_x();
+  // a missing block reads empty().x in the cases 0..6 and initValue().x in case 7 -- the same number for both
+  // field types (volume_traits.hpp:41-72), and what the pool's never-allocated payload holds
   const int xo[2] = { bx & 7, (bx + 1) & 7 };
   const int yo[2] = { (by & 7) << 3, ((by + 1) & 7) << 3 };
   const int zo[2] = { (bz & 7) << 6, ((bz + 1) & 7) << 6 };
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int off = xo[i & 1] + yo[(i >> 1) & 1] + zo[(i >> 2) & 1];
-    p[i] = (id[i] < 0) ? missing : load_x(m.block_data + (size_t)id[i] * kBlockVoxels + off);
+    p[i] = load_x(m.block_data + (size_t)id[i] * kBlockVoxels + off);
   }
 }
 
@@ -234,84 +237,140 @@ __device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c
 // Octree::grad(pos, select) (octree.hpp:652-737): central differences blended trilinearly.
 // The 48 reads of the reference expression touch 32 distinct voxels: per axis the clamped
 // coordinates {ll, lu, ul, uu} = {max(b-1,0), max(b,0), min(b+1,hi), min(b+2,hi)}, which span at most
-// two blocks per axis.  The (at most) 8 block indices are looked up once into `ids` (a per-thread
-// column of shared memory); every sample then is: pick the block by three 0/1 selectors, one load.
-// Same values and the same float expression as the reference -- only the addressing differs.
-template <class V>
-__device__ __forceinline__ V3 grad_field(const MapView<V>& m, int (*ids)[/*threads*/ 128], V3 pos) {
-  const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
-  const int b0 = (int)flx, b1 = (int)fly, b2 = (int)flz;
-  const float wx1 = pos.x - flx, wy1 = pos.y - fly, wz1 = pos.z - flz;
+// two blocks per axis.  Same values and the same float expression as the reference -- only the addressing
+// differs.  The samples, by their per-axis coordinate indices (jx, jy, jz) in 0..3 (lower = 1, upper = 2):
+//   GX(jx, y, z)  jx = 0..3, y, z in {1,2}   the four x rows of the inner 2x2 columns (16, includes the inner 2x2x2)
+//   GY(x, e, z)   jy = 0 | 3 (e = 0 | 1), x, z in {1,2}                                  (8)
+//   GZ(x, y, e)   jz = 0 | 3 (e = 0 | 1), x, y in {1,2}                                  (8)
+enum { kGradSamples = 32 };
+#define SE_GX(JX, Y, Z) ((JX) + 4 * ((Y) - 1) + 8 * ((Z) - 1))
+#define SE_GY(X, E, Z) (16 + ((X) - 1) + 2 * (E) + 4 * ((Z) - 1))
+#define SE_GZ(X, Y, E) (24 + ((X) - 1) + 2 * ((Y) - 1) + 4 * (E))
+
+// the blend of octree.hpp:669-733 over the 32 samples
+__device__ __forceinline__ V3 grad_blend(const float (&g)[kGradSamples], float wx1, float wy1, float wz1, float scale) {
   const float wx0 = 1 - wx1, wy0 = 1 - wy1, wz0 = 1 - wz1;
-  const int hi = m.size - 1;
-  // Packed per axis-coordinate code: (block selector 0/1) << 16|17|18, offset inside the block
-  // pre-scaled in the low 9 bits, bit 28+ set when the coordinate lies outside [0, hi].  (The
-  // reference clamps only one side of each coordinate -- max(b,0) can exceed hi, min(b+1,hi) can be
-  // negative when the position is outside the volume -- and then reads out of bounds; here such a
-  // sample reads initValue(), like get_fine on an unallocated block.)
-  int cx[4], cy[4], cz[4];
-  const int x4[4] = { max(b0 - 1, 0), max(b0, 0), min(b0 + 1, hi), min(b0 + 2, hi) };
-  const int y4[4] = { max(b1 - 1, 0), max(b1, 0), min(b1 + 1, hi), min(b1 + 2, hi) };
-  const int z4[4] = { max(b2 - 1, 0), max(b2, 0), min(b2 + 1, hi), min(b2 + 2, hi) };
-  int Bx = 0x7fffffff, By = 0x7fffffff, Bz = 0x7fffffff;      // lowest block touched per axis
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if ((unsigned)x4[j] <= (unsigned)hi) Bx = min(Bx, x4[j] >> 3);
-    if ((unsigned)y4[j] <= (unsigned)hi) By = min(By, y4[j] >> 3);
-    if ((unsigned)z4[j] <= (unsigned)hi) Bz = min(Bz, z4[j] >> 3);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    cx[j] = (unsigned)x4[j] <= (unsigned)hi ? ((((x4[j] >> 3) - Bx) << 16) | (x4[j] & 7)) : (1 << 28);
-    cy[j] = (unsigned)y4[j] <= (unsigned)hi ? ((((y4[j] >> 3) - By) << 17) | ((y4[j] & 7) << 3)) : (1 << 28);
-    cz[j] = (unsigned)z4[j] <= (unsigned)hi ? ((((z4[j] >> 3) - Bz) << 18) | ((z4[j] & 7) << 6)) : (1 << 28);
-  }
-  const int t = threadIdx.x;
-#pragma unroll
-  for (int s = 0; s < 8; ++s) ids[s][t] = fetch_block_cell(m, Bx + (s & 1), By + ((s >> 1) & 1), Bz + (s >> 2));
-  const float initx = FieldTraits<V>::init().x;
-#define S(JX, JY, JZ) ([&]() { const int code = cx[JX] + cy[JY] + cz[JZ]; const int id = ids[(code >> 16) & 7][t]; \
-                               return ((code >> 28) != 0 || id < 0) ? initx : load_x(m.block_data + (size_t)id * kBlockVoxels + (code & 0x1ff)); }())
-  // the 32 distinct samples (indices into {ll, lu, ul, uu} per axis: 0..3; lower = 1, upper = 2)
-  const float x_a00 = S(0, 1, 1), x_b00 = S(1, 1, 1), x_c00 = S(2, 1, 1), x_d00 = S(3, 1, 1);
-  const float x_a10 = S(0, 2, 1), x_b10 = S(1, 2, 1), x_c10 = S(2, 2, 1), x_d10 = S(3, 2, 1);
-  const float x_a01 = S(0, 1, 2), x_b01 = S(1, 1, 2), x_c01 = S(2, 1, 2), x_d01 = S(3, 1, 2);
-  const float x_a11 = S(0, 2, 2), x_b11 = S(1, 2, 2), x_c11 = S(2, 2, 2), x_d11 = S(3, 2, 2);
-  const float y_a00 = S(1, 0, 1), y_d00 = S(1, 3, 1), y_a10 = S(2, 0, 1), y_d10 = S(2, 3, 1);
-  const float y_a01 = S(1, 0, 2), y_d01 = S(1, 3, 2), y_a11 = S(2, 0, 2), y_d11 = S(2, 3, 2);
-  const float z_a00 = S(1, 1, 0), z_d00 = S(1, 1, 3), z_a10 = S(2, 1, 0), z_d10 = S(2, 1, 3);
-  const float z_a01 = S(1, 2, 0), z_d01 = S(1, 2, 3), z_a11 = S(2, 2, 0), z_d11 = S(2, 2, 3);
-#undef S
-  // inner 2x2x2 (x index 1|2, y 1|2, z 1|2) by name: x_b/x_c rows above
-  // v(x,y,z) with x,y,z in {1,2}:  v(1,1,1)=x_b00 v(2,1,1)=x_c00 v(1,2,1)=x_b10 v(2,2,1)=x_c10
-  //                                v(1,1,2)=x_b01 v(2,1,2)=x_c01 v(1,2,2)=x_b11 v(2,2,2)=x_c11
   V3 r;
   {
     // gradient(0): octree.hpp:669-689
-    const float t00 = (x_c00 - x_a00) * wx0 + (x_d00 - x_b00) * wx1;
-    const float t10 = (x_c10 - x_a10) * wx0 + (x_d10 - x_b10) * wx1;
-    const float t01 = (x_c01 - x_a01) * wx0 + (x_d01 - x_b01) * wx1;
-    const float t11 = (x_c11 - x_a11) * wx0 + (x_d11 - x_b11) * wx1;
+    const float t00 = (g[SE_GX(2, 1, 1)] - g[SE_GX(0, 1, 1)]) * wx0 + (g[SE_GX(3, 1, 1)] - g[SE_GX(1, 1, 1)]) * wx1;
+    const float t10 = (g[SE_GX(2, 2, 1)] - g[SE_GX(0, 2, 1)]) * wx0 + (g[SE_GX(3, 2, 1)] - g[SE_GX(1, 2, 1)]) * wx1;
+    const float t01 = (g[SE_GX(2, 1, 2)] - g[SE_GX(0, 1, 2)]) * wx0 + (g[SE_GX(3, 1, 2)] - g[SE_GX(1, 1, 2)]) * wx1;
+    const float t11 = (g[SE_GX(2, 2, 2)] - g[SE_GX(0, 2, 2)]) * wx0 + (g[SE_GX(3, 2, 2)] - g[SE_GX(1, 2, 2)]) * wx1;
     r.x = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
   }
   {
-    // gradient(1): octree.hpp:691-711 ; y index 0..3 at x in {1,2}
-    const float t00 = (x_b10 - y_a00) * wx0 + (x_c10 - y_a10) * wx1;     // (v(lo,ul,lo) - v(lo,ll,lo)), (v(up,ul,lo) - v(up,ll,lo))
-    const float t10 = (y_d00 - x_b00) * wx0 + (y_d10 - x_c00) * wx1;     // (v(lo,uu,lo) - v(lo,lu,lo)), (v(up,uu,lo) - v(up,lu,lo))
-    const float t01 = (x_b11 - y_a01) * wx0 + (x_c11 - y_a11) * wx1;
-    const float t11 = (y_d01 - x_b01) * wx0 + (y_d11 - x_c01) * wx1;
+    // gradient(1): octree.hpp:691-711: (v(x,ul,z) - v(x,ll,z)), (v(x,uu,z) - v(x,lu,z)) at x, z in {lower, upper}
+    const float t00 = (g[SE_GX(1, 2, 1)] - g[SE_GY(1, 0, 1)]) * wx0 + (g[SE_GX(2, 2, 1)] - g[SE_GY(2, 0, 1)]) * wx1;
+    const float t10 = (g[SE_GY(1, 1, 1)] - g[SE_GX(1, 1, 1)]) * wx0 + (g[SE_GY(2, 1, 1)] - g[SE_GX(2, 1, 1)]) * wx1;
+    const float t01 = (g[SE_GX(1, 2, 2)] - g[SE_GY(1, 0, 2)]) * wx0 + (g[SE_GX(2, 2, 2)] - g[SE_GY(2, 0, 2)]) * wx1;
+    const float t11 = (g[SE_GY(1, 1, 2)] - g[SE_GX(1, 1, 2)]) * wx0 + (g[SE_GY(2, 1, 2)] - g[SE_GX(2, 1, 2)]) * wx1;
     r.y = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
   }
   {
-    // gradient(2): octree.hpp:713-733 ; z index 0..3 at (x,y) in {1,2}^2
-    const float t00 = (x_b01 - z_a00) * wx0 + (x_c01 - z_a10) * wx1;     // y = lo: (v(lo,lo,ul) - v(lo,lo,ll)), (v(up,lo,ul) - v(up,lo,ll))
-    const float t10 = (x_b11 - z_a01) * wx0 + (x_c11 - z_a11) * wx1;     // y = up
-    const float t01 = (z_d00 - x_b00) * wx0 + (z_d10 - x_c00) * wx1;     // y = lo: (v(lo,lo,uu) - v(lo,lo,lu)), ...
-    const float t11 = (z_d01 - x_b10) * wx0 + (z_d11 - x_c10) * wx1;     // y = up
+    // gradient(2): octree.hpp:713-733: (v(x,y,ul) - v(x,y,ll)), (v(x,y,uu) - v(x,y,lu)) at x, y in {lower, upper}
+    const float t00 = (g[SE_GX(1, 1, 2)] - g[SE_GZ(1, 1, 0)]) * wx0 + (g[SE_GX(2, 1, 2)] - g[SE_GZ(2, 1, 0)]) * wx1;
+    const float t10 = (g[SE_GX(1, 2, 2)] - g[SE_GZ(1, 2, 0)]) * wx0 + (g[SE_GX(2, 2, 2)] - g[SE_GZ(2, 2, 0)]) * wx1;
+    const float t01 = (g[SE_GZ(1, 1, 1)] - g[SE_GX(1, 1, 1)]) * wx0 + (g[SE_GZ(2, 1, 1)] - g[SE_GX(2, 1, 1)]) * wx1;
+    const float t11 = (g[SE_GZ(1, 2, 1)] - g[SE_GX(1, 2, 1)]) * wx0 + (g[SE_GZ(2, 2, 1)] - g[SE_GX(2, 2, 1)]) * wx1;
     r.z = (t00 * wy0 + t10 * wy1) * wz0 + (t01 * wy0 + t11 * wy1) * wz1;
   }
-  const float s = (0.5f * m.dim) / (float)m.size;
-  return v3(s * r.x, s * r.y, s * r.z);
+  return v3(scale * r.x, scale * r.y, scale * r.z);
+}
+
+// The general gather, for positions on or beyond the volume's faces (some clamped coordinate lies outside
+// [0, hi]: the reference clamps only one side of each -- max(b,0) can exceed hi, min(b+1,hi) can be negative --
+// and then reads out of bounds; here such a sample reads initValue(), like get_fine on an unallocated block)
+// and for pools too large for 32-bit voxel indices.  Out of line: rays almost never end there.
+template <class V>
+__device__ __noinline__ V3 grad_field_general(const MapView<V>& m, int b0, int b1, int b2, float wx1, float wy1, float wz1, float scale) {
+  float g[kGradSamples];
+  const int hi = m.size - 1;
+  const int x4[4] = { max(b0 - 1, 0), max(b0, 0), min(b0 + 1, hi), min(b0 + 2, hi) };
+  const int y4[4] = { max(b1 - 1, 0), max(b1, 0), min(b1 + 1, hi), min(b1 + 2, hi) };
+  const int z4[4] = { max(b2 - 1, 0), max(b2, 0), min(b2 + 1, hi), min(b2 + 2, hi) };
+  const float initx = FieldTraits<V>::init().x;
+  auto sample = [&](int jx, int jy, int jz) -> float {
+    const int x = x4[jx], y = y4[jy], z = z4[jz];
+    if (!in_volume(m, x, y, z)) return initx;
+    const int id = fetch_block(m, x, y, z);
+    return id < 0 ? initx : load_x(m.block_data + (size_t)id * kBlockVoxels + voxel_offset<V>(x, y, z));
+  };
+  for (int z = 1; z <= 2; ++z)
+    for (int y = 1; y <= 2; ++y)
+      for (int jx = 0; jx < 4; ++jx) g[SE_GX(jx, y, z)] = sample(jx, y, z);
+  for (int z = 1; z <= 2; ++z)
+    for (int e = 0; e < 2; ++e)
+      for (int x = 1; x <= 2; ++x) g[SE_GY(x, e, z)] = sample(x, 3 * e, z);
+  for (int e = 0; e < 2; ++e)
+    for (int y = 1; y <= 2; ++y)
+      for (int x = 1; x <= 2; ++x) g[SE_GZ(x, y, e)] = sample(x, y, 3 * e);
+  return grad_blend(g, wx1, wy1, wz1, scale);
+}
+
+// The usual case -- the whole 4x4x4 neighbourhood inside the volume -- in 12 rows: a row is the run of samples
+// that differ only in x; its (at most two) blocks come as one int2 from a per-thread shared-memory column
+// (`pairs[sy + 2 sz][thread]` = block ids at x-block 0 and 1, unallocated ones replaced by the pool's
+// never-allocated initValue() block, so no sample needs a validity test), and every sample then is one select,
+// one add, one load.
+template <class V>
+__device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*threads*/ 128], V3 pos) {
+  const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
+  const int b0 = (int)flx, b1 = (int)fly, b2 = (int)flz;
+  const float scale = (0.5f * m.dim) / (float)m.size;
+  const int hi = m.size - 1;
+  // every clamped coordinate inside [0, hi]  <=>  -1 <= b <= hi on each axis
+  const bool inside = ((unsigned)(b0 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b1 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b2 + 1) <= (unsigned)(hi + 1));
+  if (!inside || m.max_blocks >= (1 << 22)) return grad_field_general(m, b0, b1, b2, pos.x - flx, pos.y - fly, pos.z - flz, scale);
+  float g[kGradSamples];
+  const int x4[4] = { max(b0 - 1, 0), max(b0, 0), min(b0 + 1, hi), min(b0 + 2, hi) };
+  const int y4[4] = { max(b1 - 1, 0), max(b1, 0), min(b1 + 1, hi), min(b1 + 2, hi) };
+  const int z4[4] = { max(b2 - 1, 0), max(b2, 0), min(b2 + 1, hi), min(b2 + 2, hi) };
+  const int Bx = x4[0] >> 3, By = y4[0] >> 3, Bz = z4[0] >> 3;      // the coordinates are non-decreasing: lowest block per axis
+  int sx[4], ox[4], ry[4], oy[4], rz[4], oz[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sx[j] = (x4[j] >> 3) - Bx;        ox[j] = x4[j] & 7;
+    ry[j] = (y4[j] >> 3) - By;        oy[j] = (y4[j] & 7) << 3;
+    rz[j] = ((z4[j] >> 3) - Bz) << 1; oz[j] = (z4[j] & 7) << 6;
+  }
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int lo = fetch_block_cell(m, Bx, By + (r & 1), Bz + (r >> 1)), up = fetch_block_cell(m, Bx + 1, By + (r & 1), Bz + (r >> 1));
+    pairs[r][t] = make_int2(lo < 0 ? m.max_blocks : lo, up < 0 ? m.max_blocks : up);
+  }
+  struct Row { int lo, up; };
+  auto row = [&](int jy, int jz) {
+    const int2 pr = pairs[ry[jy] + rz[jz]][t];
+    const int o = oy[jy] + oz[jz];
+    Row r; r.lo = pr.x * kBlockVoxels + o; r.up = pr.y * kBlockVoxels + o;
+    return r;
+  };
+  auto S = [&](const Row& r, int jx) { return load_x(m.block_data + ((sx[jx] ? r.up : r.lo) + ox[jx])); };
+#pragma unroll
+  for (int z = 1; z <= 2; ++z)
+#pragma unroll
+    for (int y = 1; y <= 2; ++y) {
+      const Row r = row(y, z);
+#pragma unroll
+      for (int jx = 0; jx < 4; ++jx) g[SE_GX(jx, y, z)] = S(r, jx);
+    }
+#pragma unroll
+  for (int z = 1; z <= 2; ++z)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const Row r = row(3 * e, z);
+      g[SE_GY(1, e, z)] = S(r, 1); g[SE_GY(2, e, z)] = S(r, 2);
+    }
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+#pragma unroll
+    for (int y = 1; y <= 2; ++y) {
+      const Row r = row(y, 3 * e);
+      g[SE_GZ(1, y, e)] = S(r, 1); g[SE_GZ(2, y, e)] = S(r, 2);
+    }
+  return grad_blend(g, pos.x - flx, pos.y - fly, pos.z - flz, scale);
 }
 
 // VolumeTemplate::{get,interp,grad} (se_denseslam/include/se/continuous/volume_template.hpp:77-102):
@@ -329,7 +388,7 @@ __device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, 
   return interp_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
 }
 template <class V>
-__device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, int (*ids)[128], V3 p) {
+__device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, int2 (*ids)[128], V3 p) {
   c.n_grad++;
   const float inv = (float)m.size / m.dim;
   return grad_field(m, ids, v3(inv * p.x, inv * p.y, inv * p.z));
