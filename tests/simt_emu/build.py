@@ -50,9 +50,16 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, defines=(), suffix: str = "") -> str:
+    """defines / suffix: a build of a compile-time variant (e.g. ("-DSE_INT_STAGE_SLICES=4",), "_half") next to the default one"""
+    if suffix:
+        return _build(LIB.replace(".so", suffix + ".so"), tuple(defines))
     if not force and up_to_date():
         return LIB
+    return _build(LIB, tuple(defines))
+
+
+def _build(lib: str, defines) -> str:
     src = os.path.join(BUILD, "supereight_b200", "csrc")      # same depth as the original: "../../include/se_b200.h" resolves
     os.makedirs(src, exist_ok=True)
     os.makedirs(os.path.join(BUILD, "include"), exist_ok=True)
@@ -68,10 +75,10 @@ def build(force: bool = False) -> str:
             fh.write(text)
     shutil.copy(os.path.join(HERE, "se_ptx_emu.cuh"), os.path.join(src, "se_ptx.cuh"))
     cmd = ["g++", "-std=c++17", "-O2", "-g1", "-fPIC", "-shared", "-ffp-contract=off", "-mfma", "-fno-strict-aliasing",
-           "-Wno-attributes", "-Wno-unused-value", "-I", os.path.join(HERE, "include"), "-x", "c++", os.path.join(src, "se_b200.cu"),
-           "-o", LIB]
+           "-Wno-attributes", "-Wno-unused-value", *defines, "-I", os.path.join(HERE, "include"), "-x", "c++", os.path.join(src, "se_b200.cu"),
+           "-o", lib]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

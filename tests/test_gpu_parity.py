@@ -380,6 +380,33 @@ def test_sdf_ieee_division_fallback_paths(monkeypatch):
     assert_sdf_bit_exact(g, o, pose, k, mu)
 
 
+def test_ofusion_plain_operator_instantiation(monkeypatch):
+    """OFusion integrates with the check-free sequences and the tabulated log-odds increment by default; the
+    instantiation with the plain IEEE operators and the per-voxel log2 (SE_B200_OFUSION_FAST=0, or SE_B200_IEEE_DIV)
+    must match the oracle just the same and leave the same map.  (Byte equality of the two instantiations is asserted on
+    the fiber executor, tests/test_simt_emu.py; here, with the device's own MUFU approximations underneath, the bar is
+    the one the 1024^3 test applies against the oracle: timestamps equal, < 1e-3 of the values off by an ulp.)"""
+    from supereight_b200 import synth
+    dim, mu, W, H = 4.8, 0.008, 160, 120
+    k = scaled_k(W)
+    maps = []
+    for env in (None, "SE_B200_OFUSION_FAST", "SE_B200_IEEE_DIV"):
+        if env:
+            monkeypatch.setenv(env, "0" if env.endswith("FAST") else "1")
+        g, o = make_pair(OFUSION, 256, dim, W, H)
+        pose = run_sequence(g, o, synth.box_room, dim, W, H, k, mu, range(0, 12, 4), n_frames=300, dropout=0.01)
+        assert assert_ofusion_parity(g, o, pose, k, mu) < 1e-3
+        maps.append(g.blocks_sorted())
+        if env:
+            monkeypatch.delenv(env)
+    k0, c0, a0, d0 = maps[0]
+    for k1, c1, a1, d1 in maps[1:]:
+        assert np.array_equal(k0, k1) and np.array_equal(c0, c1) and np.array_equal(a0, a1)
+        assert np.array_equal(d0["y"], d1["y"])
+        assert np.count_nonzero(d0["x"].view(np.uint32) != d1["x"].view(np.uint32)) < 1e-3 * d0["x"].size
+        np.testing.assert_allclose(d0["x"], d1["x"], rtol=REL_TOL, atol=1e-5)
+
+
 def test_ragged_image_sizes_and_tiny_volume():
     """Image sizes that are not multiples of the 8x4 pixel tile, and the smallest supported volume."""
     from supereight_b200 import synth

@@ -42,6 +42,7 @@ FAST_GPU_TESTS = [
     "tests/test_gpu_parity.py::test_sdf_camera_outside_and_partially_out_of_volume",
     "tests/test_gpu_parity.py::test_sdf_weight_saturation_property",
     "tests/test_gpu_parity.py::test_sdf_ieee_division_fallback_paths",
+    "tests/test_gpu_parity.py::test_ofusion_plain_operator_instantiation",
     "tests/test_gpu_parity.py::test_ragged_image_sizes_and_tiny_volume",
     "tests/test_gpu_parity.py::test_error_paths_and_render_track",
     "tests/test_gpu_parity.py::test_map_export_import_round_trip",
@@ -63,6 +64,15 @@ def test_tree_descent_without_the_directories(emu_lib):
     run_pytest_on_emu(emu_lib, "tests/test_gpu_parity.py::test_map_export_import_round_trip", {"SE_B200_DISABLE_DIRECTORY": "1"})
 
 
+def test_staged_integrate_experiment_is_bit_exact(emu_lib):
+    """csrc/se_integrate_staged.cuh (opt-in, -DSE_INT_STAGE_SLICES=4: half-block pipeline stages, 4 CTAs per SM): the same
+    SDF parity tests on a build with the define, so that the variant is ready for its A/B on the device."""
+    import build as simt_build
+    lib = simt_build.build(defines=("-DSE_INT_STAGE_SLICES=4",), suffix="_stage4")
+    run_pytest_on_emu(lib, "tests/test_gpu_parity.py::test_sdf_512_full_frame_sequence_bit_exact")
+    run_pytest_on_emu(lib, "tests/test_gpu_parity.py::test_sdf_ieee_division_fallback_paths")
+
+
 def run_worker(emu_lib, field, out, extra_env):
     env = dict(os.environ, SE_B200_LIB=emu_lib, **extra_env)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_simt_worker.py"), field, out], env=env, capture_output=True, text=True, timeout=600)
@@ -74,7 +84,7 @@ def run_worker(emu_lib, field, out, extra_env):
 def test_check_free_arithmetic_gives_the_ieee_bits(emu_lib, tmp_path, field):
     """The integrate kernels' check-free division / square-root sequences (and, for OFusion, the tabulated log-odds
     increment) against the instantiation with the plain IEEE operators: every array identical, bit for bit."""
-    fast = run_worker(emu_lib, field, str(tmp_path / "fast.npz"), {"SE_B200_OFUSION_FAST": "1"})
+    fast = run_worker(emu_lib, field, str(tmp_path / "fast.npz"), {})
     ieee = run_worker(emu_lib, field, str(tmp_path / "ieee.npz"), {"SE_B200_IEEE_DIV": "1"})
     assert len(fast["keys"]) > 500 and (fast["normal"][..., 0] != -2.0).sum() > 5000
     for name in fast.files:
