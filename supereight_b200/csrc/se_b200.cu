@@ -556,7 +556,10 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
     CREATE_TRY(cudaMalloc(&m->d_requests, (size_t)m->max_requests * sizeof(unsigned long long)));
     float lut[1000];
     make_bspline_lut(lut);
-    CREATE_TRY(cudaMemcpyToSymbol(c_bspline_lut, lut, sizeof(lut)));
+    // on the map's stream: ordered before k_fill_logodds below and before every integrate (the map's stream is
+    // non-blocking, so a copy on the legacy default stream would not be); create_pools ends with a synchronisation,
+    // so `lut` outlives the copy
+    CREATE_TRY(cudaMemcpyToSymbolAsync(c_bspline_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, m->stream));
     const int ncell = kLogOddsDim * kLogOddsDim;
     CREATE_TRY(cudaMalloc(&m->d_logodds, (size_t)ncell * sizeof(float)));
     k_fill_logodds<<<(ncell + 255) / 256, 256, 0, m->stream>>>(m->d_logodds);

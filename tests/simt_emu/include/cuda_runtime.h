@@ -383,6 +383,9 @@ inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) 
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* s, size_t n) { std::memcpy(&sym, s, n); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMemcpyToSymbolAsync(T& sym, const void* s, size_t n, size_t off, cudaMemcpyKind, cudaStream_t = nullptr) {
+  std::memcpy((char*)&sym + off, s, n); return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)std::malloc(1); return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
