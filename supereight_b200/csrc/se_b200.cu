@@ -552,13 +552,12 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
   CREATE_TRY(cudaMemsetAsync(m->d_depth, 0, npx * sizeof(float), m->stream));
   CREATE_TRY(cudaMemsetAsync(m->d_vertex, 0, npx * 3 * sizeof(float), m->stream));
   CREATE_TRY(cudaMemsetAsync(m->d_normal, 0, npx * 3 * sizeof(float), m->stream));
+  float lut[1000];      // function scope: it outlives the stream-ordered copy below (create_pools ends with a synchronisation)
   if (field_type == SE_B200_OFUSION) {
     CREATE_TRY(cudaMalloc(&m->d_requests, (size_t)m->max_requests * sizeof(unsigned long long)));
-    float lut[1000];
     make_bspline_lut(lut);
     // on the map's stream: ordered before k_fill_logodds below and before every integrate (the map's stream is
-    // non-blocking, so a copy on the legacy default stream would not be); create_pools ends with a synchronisation,
-    // so `lut` outlives the copy
+    // non-blocking, so a copy on the legacy default stream would not be)
     CREATE_TRY(cudaMemcpyToSymbolAsync(c_bspline_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, m->stream));
     const int ncell = kLogOddsDim * kLogOddsDim;
     CREATE_TRY(cudaMalloc(&m->d_logodds, (size_t)ncell * sizeof(float)));
