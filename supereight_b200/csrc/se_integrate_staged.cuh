@@ -6,7 +6,7 @@
 // headline workload then take one round of the 4 736 resident warps instead of 1.3 rounds of 3 552.
 // State: bit-exact in the CPU test tier (all SDF parity tests, library built with the define); with 8 slices the
 // SASS has the same opcode histogram as the default kernel.  NOT yet timed or run on the device: the round's GPU budget
-// ran out (the A/B is scripts/ab_stage.sh).  Included by se_kernels.cuh in place of the default kernel when the macro is set.
+// ran out (the A/B is scripts/build_variants.sh + scripts/ab_variants.sh).  Included by se_kernels.cuh in place of the default kernel when the macro is set.
 #pragma once
 
 constexpr int kIntegrateWarps = 8;                        // warps per CTA

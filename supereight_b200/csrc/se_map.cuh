@@ -335,6 +335,25 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*th
     rz[j] = ((z4[j] >> 3) - Bz) << 1; oz[j] = (z4[j] & 7) << 6;
   }
   const int t = threadIdx.x;
+#ifdef SE_GRAD_NBHD
+  // EXPERIMENT (opt-in, not in the default build): the 2x2x2 directory cells from one base index.
+  // (Bx, By, Bz) is inside the grid here, only the +1 cells can fall outside it: such a cell re-reads an inside one
+  // and the value is discarded.  Eight generic lookups cost ~31 instructions each (three bounds tests, the index
+  // arithmetic, the directory test); this is ~8 per cell.
+  if (m.dir) {
+    const int G = m.dir_dim;
+    const bool ux = Bx + 1 < G, uy = By + 1 < G, uz = Bz + 1 < G;
+    const int base = (Bz * G + By) * G + Bx;
+    const int dxo = ux ? 1 : 0, dyo = uy ? G : 0, dzo = uz ? G * G : 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int cell = base + ((r & 1) ? dyo : 0) + ((r >> 1) ? dzo : 0);
+      const bool row_ok = ((r & 1) ? uy : true) & ((r >> 1) ? uz : true);
+      const int lo = __ldg(m.dir + cell), up = __ldg(m.dir + cell + dxo);
+      pairs[r][t] = make_int2((row_ok && lo >= 0) ? lo : m.max_blocks, (row_ok && ux && up >= 0) ? up : m.max_blocks);
+    }
+  } else
+#endif
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int lo = fetch_block_cell(m, Bx, By + (r & 1), Bz + (r >> 1)), up = fetch_block_cell(m, Bx + 1, By + (r & 1), Bz + (r >> 1));

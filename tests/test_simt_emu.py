@@ -64,13 +64,24 @@ def test_tree_descent_without_the_directories(emu_lib):
     run_pytest_on_emu(emu_lib, "tests/test_gpu_parity.py::test_map_export_import_round_trip", {"SE_B200_DISABLE_DIRECTORY": "1"})
 
 
-def test_staged_integrate_experiment_is_bit_exact(emu_lib):
-    """csrc/se_integrate_staged.cuh (opt-in, -DSE_INT_STAGE_SLICES=4: half-block pipeline stages, 4 CTAs per SM): the same
-    SDF parity tests on a build with the define, so that the variant is ready for its A/B on the device."""
+EXPERIMENTS = [
+    # csrc/se_integrate_staged.cuh: half-block pipeline stages, 4 CTAs per SM
+    ("-DSE_INT_STAGE_SLICES=4", "_stage4", ["tests/test_gpu_parity.py::test_sdf_512_full_frame_sequence_bit_exact",
+                                            "tests/test_gpu_parity.py::test_sdf_ieee_division_fallback_paths"]),
+    # se_map.cuh grad_field: the gradient's 2x2x2 directory cells from one base index
+    ("-DSE_GRAD_NBHD", "_nbhd", ["tests/test_gpu_parity.py::test_point_queries_match_oracle_all_gather_cases",
+                                 "tests/test_gpu_parity.py::test_sdf_camera_outside_and_partially_out_of_volume"]),
+]
+
+
+@pytest.mark.parametrize("define,suffix,nodeids", EXPERIMENTS, ids=[e[1][1:] for e in EXPERIMENTS])
+def test_opt_in_experiments_are_bit_exact(emu_lib, define, suffix, nodeids):
+    """The compile-time experiments (not in the default build) stay bit-exact against the oracle, so
+    that each is ready for its A/B on the device: the parity tests on a build of the library with the define."""
     import build as simt_build
-    lib = simt_build.build(defines=("-DSE_INT_STAGE_SLICES=4",), suffix="_stage4")
-    run_pytest_on_emu(lib, "tests/test_gpu_parity.py::test_sdf_512_full_frame_sequence_bit_exact")
-    run_pytest_on_emu(lib, "tests/test_gpu_parity.py::test_sdf_ieee_division_fallback_paths")
+    lib = simt_build.build(defines=(define,), suffix=suffix)
+    for nodeid in nodeids:
+        run_pytest_on_emu(lib, nodeid)
 
 
 def run_worker(emu_lib, field, out, extra_env):
