@@ -19,11 +19,13 @@ for line in sys.stdin:
 }
 for rep in 1 2; do
   run "" planar_sweep_sdf512 200
-  for v in stage4 nbhd both; do run $PWD/ab_libs/$v.so planar_sweep_sdf512 200; done
+  for v in stage4 nbhd uni ray all; do run $PWD/ab_libs/$v.so planar_sweep_sdf512 200; done
 done
 run "" box_room_sdf2048 60
-for v in stage4 both; do run $PWD/ab_libs/$v.so box_room_sdf2048 60; done
-for v in stage4 nbhd both; do
+for v in stage4 all; do run $PWD/ab_libs/$v.so box_room_sdf2048 60; done
+run "" box_room_ofusion1024 60
+run $PWD/ab_libs/ray.so box_room_ofusion1024 60
+for v in stage4 ray all; do
   (echo "== parity on $v"; SE_B200_LIB=$PWD/ab_libs/$v.so timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sdf_512_full or sdf_2048 or ieee_division or point_queries or ofusion_plane" 2>&1 | tail -3) >> $LOG 2>&1
 done
 cat $LOG

@@ -339,6 +339,13 @@ RaycastParams make_raycast_params(se_b200_map* m, const float* pose, const float
   rp.step = m->dim / (float)m->size;                                      // DenseSLAMSystem.cpp:197, :282
   rp.largestep = largestep;
   rp.W = m->W; rp.H = m->H; rp.use_tcmin = use_tcmin;
+#ifdef SE_RAY_UNIFORMS
+  // the same single-rounding IEEE operations RayWalk::init performs per thread (this file is compiled without FMA contraction)
+  rp.so = v3(rp.view.m[3] / m->dim + 1.f, rp.view.m[7] / m->dim + 1.f, rp.view.m[11] / m->dim + 1.f);
+  rp.eps = 1.0f / (float)m->size;
+  rp.near_n = rp.nearPlane / m->dim;
+  rp.far_n = rp.farPlane / m->dim;
+#endif
   return rp;
 }
 
