@@ -321,7 +321,14 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*th
   const int hi = m.size - 1;
   // every clamped coordinate inside [0, hi]  <=>  -1 <= b <= hi on each axis
   const bool inside = ((unsigned)(b0 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b1 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b2 + 1) <= (unsigned)(hi + 1));
-  if (!inside || m.max_blocks >= (1 << 22)) return grad_field_general(m, b0, b1, b2, pos.x - flx, pos.y - fly, pos.z - flz, scale);
+#ifdef SE_GRAD_NBHD
+  typedef unsigned VoxelIndex;      // experiment: block * 512 + offset as unsigned -> pools up to 2^23 - 1 blocks stay on this path
+  const int kIndexablePool = (1 << 23) - 1;
+#else
+  typedef int VoxelIndex;
+  const int kIndexablePool = (1 << 22) - 1;
+#endif
+  if (!inside || m.max_blocks > kIndexablePool) return grad_field_general(m, b0, b1, b2, pos.x - flx, pos.y - fly, pos.z - flz, scale);
   float g[kGradSamples];
   const int x4[4] = { max(b0 - 1, 0), max(b0, 0), min(b0 + 1, hi), min(b0 + 2, hi) };
   const int y4[4] = { max(b1 - 1, 0), max(b1, 0), min(b1 + 1, hi), min(b1 + 2, hi) };
@@ -359,11 +366,11 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*th
     const int lo = fetch_block_cell(m, Bx, By + (r & 1), Bz + (r >> 1)), up = fetch_block_cell(m, Bx + 1, By + (r & 1), Bz + (r >> 1));
     pairs[r][t] = make_int2(lo < 0 ? m.max_blocks : lo, up < 0 ? m.max_blocks : up);
   }
-  struct Row { int lo, up; };
+  struct Row { VoxelIndex lo, up; };
   auto row = [&](int jy, int jz) {
     const int2 pr = pairs[ry[jy] + rz[jz]][t];
     const int o = oy[jy] + oz[jz];
-    Row r; r.lo = pr.x * kBlockVoxels + o; r.up = pr.y * kBlockVoxels + o;
+    Row r; r.lo = (VoxelIndex)pr.x * kBlockVoxels + o; r.up = (VoxelIndex)pr.y * kBlockVoxels + o;
     return r;
   };
   auto S = [&](const Row& r, int jx) { return load_x(m.block_data + ((sx[jx] ? r.up : r.lo) + ox[jx])); };
