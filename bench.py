@@ -371,6 +371,29 @@ def run_gpu(args, cfg, rank, world, local_rank):
         ov_failed, ov_note = 1.0, f"{type(e).__name__}: {e}"
     barrier()
 
+    # ---------------- e2e with a render target (opt-in: SE_B200_BENCH_RENDER_TARGET=1) ----------------
+    # The synchronous loop of `e2e`, with se_b200_set_render_target(the pinned output buffer) called once before it: the raycast
+    # kernel shades and writes the image over PCIe as the rays finish, se_b200_render_volume_host only synchronises.
+    # Off by default until the extension has been run on the device.
+    rt_s, rt_note = 0.0, "not requested (SE_B200_BENCH_RENDER_TARGET=1 runs it)"
+    if os.environ.get("SE_B200_BENCH_RENDER_TARGET") == "1":
+        try:
+            m = new_map()
+            m.set_stage_timing(False)
+            h_rgba.zero_()
+            check(lib.se_b200_set_render_target(m.h, hrgba_ptr))
+            for f in range(warmup):
+                flush.zero_(); step_host(f)
+            for i in range(steps):
+                flush.zero_(); torch.cuda.synchronize()
+                t0 = time.perf_counter(); step_host(warmup + i); rt_s += time.perf_counter() - t0
+            rt_checksum = int(h_rgba.numpy().astype(np.uint64).sum())
+            rt_note = None if rt_checksum == checksum else f"last image differs from the plain run ({rt_checksum} vs {checksum})"
+            m.close()
+        except Exception as e:
+            rt_note = f"{type(e).__name__}: {e}"
+        barrier()
+
     # ---------------- aggregate: max over ranks ----------------
     total_ms_max, e2e_ms_max, ov_ms_max, ov_failed_any = max_over_ranks([total_ms, e2e_s * 1e3, ov_s * 1e3, ov_failed], world, dev)
     result = None
@@ -409,6 +432,9 @@ def run_gpu(args, cfg, rank, world, local_rank):
                                 "api": "se_b200_preprocess_depth_host_async + se_b200_render_volume_host_async (copy streams, double-buffered); "
                                        "same bytes per step as e2e, frames issued back to back, one synchronisation at the end, no L2 flush"}
                                if ov_failed_any == 0 and ov_ms_max > 0 else {"unavailable": ov_note or "failed on another rank"}),
+            "e2e_render_target": ({"value": round(steps / rt_s, 2), "unit": UNIT, "ms_per_step": round(1e3 * rt_s / steps, 5), "scope": "rank 0",
+                                   "api": "the e2e loop after se_b200_set_render_target(pinned out): raycast shades and writes the image in place"}
+                                  if rt_note is None and rt_s > 0 else {"unavailable": rt_note}),
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",

@@ -102,6 +102,17 @@ int se_b200_render_volume_device(se_b200_map* map, uint8_t* out_dev, const float
                                  float mu, float largestep, int reraycast);
 int se_b200_render_depth_host(se_b200_map* map, uint8_t* out);
 
+/* Extension (no counterpart in the reference, whose renderVolume always runs after raycasting has returned): while a render
+ * target is set, se_b200_raycast also shades every pixel exactly as renderVolume's reuse path would (rendering.cpp:259-279,
+ * light at the raycast pose) and stores the RGBA image to `out` as each ray finishes.  `out` is W*H*4 bytes of device memory
+ * or of PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister: its mapped alias is written in place, so the image crosses
+ * PCIe while the remaining rays are still being cast); NULL turns the mode off.  se_b200_render_volume_host / _device called
+ * with that same pointer, reraycast == 0 and a view pose whose translation is the raycast pose's then launch nothing:
+ * _host only synchronises, _device returns (the image is there in stream order).  Any other call renders as usual.
+ * The caller must keep `out` valid, and leave its contents alone between the raycast and the render call, until the target is
+ * changed or the map destroyed. */
+int se_b200_set_render_target(se_b200_map* map, uint8_t* out);
+
 /* ---- overlapped host I/O (no counterpart in the reference, whose stages are synchronous) ----------------
  * The same two stages as se_b200_preprocess_depth_host / se_b200_render_volume_host, but the copies run on the map's own
  * upload / download streams through double-buffered staging in HBM, ordered against the kernel stream by events:

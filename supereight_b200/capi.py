@@ -26,7 +26,7 @@ EXPORTS = (
     "se_b200_download_nodes_sorted", "se_b200_upload_blocks", "se_b200_upload_nodes", "se_b200_allocate_keys", "se_b200_query_voxels", "se_b200_query_interp",
     "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_set_stage_timing", "se_b200_counters",
     "se_b200_launch_count", "se_b200_device_image", "se_b200_extract_mesh", "se_b200_download_mesh", "se_b200_mc_table",
-    "se_b200_preprocess_depth_host_async", "se_b200_render_volume_host_async",
+    "se_b200_preprocess_depth_host_async", "se_b200_render_volume_host_async", "se_b200_set_render_target",
 )
 
 
@@ -68,6 +68,7 @@ def load_library():
     lib.se_b200_render_volume_host_async.argtypes = [vp, vp, vp, vp, f32, f32, i32]
     lib.se_b200_render_volume_device.argtypes = [vp, vp, vp, vp, f32, f32, i32]
     lib.se_b200_render_depth_host.argtypes = [vp, vp]
+    lib.se_b200_set_render_target.argtypes = [vp, vp]
     lib.se_b200_render_track_host.argtypes = [vp, vp, vp, i32]
     lib.se_b200_filter_depth.argtypes = [vp, i32, i32]
     lib.se_b200_track.argtypes = [vp, vp, vp, vp, f32, vp, i32, C.POINTER(i32)]
@@ -196,6 +197,10 @@ class Map:
     def render_volume_device_ptr(self, out_ptr: int, view_pose, k, mu, largestep, reraycast: bool):
         p, kk = _f32(view_pose, 16), _f32(k, 4)
         self._check(self.lib.se_b200_render_volume_device(self.h, C.c_void_p(out_ptr), _ptr(p), _ptr(kk), mu, largestep, int(reraycast)))
+
+    def set_render_target(self, out_ptr):
+        """se_b200_set_render_target: `out_ptr` = address of W*H*4 bytes of device or pinned host memory, or None / 0 to turn it off"""
+        self._check(self.lib.se_b200_set_render_target(self.h, C.c_void_p(out_ptr or None)))
 
     def render_depth(self):
         out = np.empty((self.H, self.W, 4), np.uint8)

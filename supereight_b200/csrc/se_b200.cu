@@ -104,6 +104,12 @@ struct se_b200_map {
   } aio;
   cudaEvent_t ev_begin[SE_B200_NUM_STAGES] = {}, ev_end[SE_B200_NUM_STAGES] = {};
   bool ev_valid[SE_B200_NUM_STAGES] = {};
+  // se_b200_set_render_target: the raycast also shades into rt_dev (device memory or the mapped alias of the caller's
+  // pinned buffer rt_user); rt_valid = the last raycast filled it, with the light at rt_light
+  uchar4* rt_dev = nullptr;
+  const void* rt_user = nullptr;
+  bool rt_valid = false;
+  float rt_light[3] = {0.f, 0.f, 0.f};
   long long launches = 0;
   int grid_integrate = 0;
   int parity = 0;
@@ -354,11 +360,23 @@ int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu, un
   const float step = m->dim / (float)m->size;
   const RaycastParams rp = make_raycast_params(m, pose, k, mu, kFarPlane, step * (float)kBlockSide, 1);
   stage_begin(m, SE_B200_STAGE_RAYCAST);
-  if (stats_dev) launch_pdl(k_raycast<V, true>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
+  m->rt_valid = false;
+  if (m->rt_dev && !stats_dev) {
+    const V3 light = v3(pose[3], pose[7], pose[11]);           // the reuse path's light: view pose == raycast pose
+    launch_pdl(k_raycast_shade<V>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, light, m->rt_dev);
+    m->rt_light[0] = pose[3]; m->rt_light[1] = pose[7]; m->rt_light[2] = pose[11];
+    m->rt_valid = true;
+  } else if (stats_dev) launch_pdl(k_raycast<V, true>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
   else launch_pdl(k_raycast<V, false>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RAYCAST);
   return SE_B200_OK;
+}
+
+// true when the last raycast already rendered the reuse-path image of this view into the caller's render target
+bool render_target_holds(const se_b200_map* m, const void* out, const float* view_pose, int reraycast) {
+  return !reraycast && m->rt_valid && out && (out == m->rt_user || out == (const void*)m->rt_dev) &&
+         view_pose[3] == m->rt_light[0] && view_pose[7] == m->rt_light[1] && view_pose[11] == m->rt_light[2];
 }
 
 template <class V>
@@ -777,6 +795,7 @@ int se_b200_upload_vertex_normal(se_b200_map* m, const float* vertex, const floa
   REQUIRE_MAP(m);
   DeviceGuard guard(m->device);
   const size_t bytes = (size_t)m->W * m->H * 3 * sizeof(float);
+  m->rt_valid = false;
   if (vertex) CUDA_TRY(cudaMemcpyAsync(m->d_vertex, vertex, bytes, cudaMemcpyHostToDevice, m->stream));
   if (normal) CUDA_TRY(cudaMemcpyAsync(m->d_normal, normal, bytes, cudaMemcpyHostToDevice, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -787,6 +806,7 @@ int se_b200_render_volume_device(se_b200_map* m, uint8_t* out_dev, const float v
                                  float mu, float largestep, int reraycast) {
   REQUIRE_MAP(m);
   if (!out_dev || !view_pose || !k) return fail(SE_B200_ERR_ARG, "null argument");
+  if (render_target_holds(m, out_dev, view_pose, reraycast)) return SE_B200_OK;      // se_b200_set_render_target: already there, in stream order
   DeviceGuard guard(m->device);
   return FIELD_DISPATCH(m, render_volume_impl<SdfVoxel>(m, (uchar4*)out_dev, view_pose, k, mu, largestep, reraycast),
                         render_volume_impl<OfuVoxel>(m, (uchar4*)out_dev, view_pose, k, mu, largestep, reraycast));
@@ -796,7 +816,12 @@ int se_b200_render_volume_host(se_b200_map* m, uint8_t* out, const float view_po
                                float mu, float largestep, int reraycast) {
   REQUIRE_MAP(m);
   if (!out) return fail(SE_B200_ERR_ARG, "out is null");
+  if (!view_pose || !k) return fail(SE_B200_ERR_ARG, "null argument");
   DeviceGuard guard(m->device);
+  if (render_target_holds(m, out, view_pose, reraycast)) {      // se_b200_set_render_target: the raycast wrote it; wait for it
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return SE_B200_OK;
+  }
   if (void* alias = mapped_alias(out)) {            // pinned destination: the shading kernel writes it in place
     if (int r = se_b200_render_volume_device(m, (uint8_t*)alias, view_pose, k, mu, largestep, reraycast)) return r;
   } else {
@@ -804,6 +829,22 @@ int se_b200_render_volume_host(se_b200_map* m, uint8_t* out, const float view_po
     CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)m->W * m->H * 4, cudaMemcpyDeviceToHost, m->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return SE_B200_OK;
+}
+
+int se_b200_set_render_target(se_b200_map* m, uint8_t* out) {
+  REQUIRE_MAP(m);
+  DeviceGuard guard(m->device);
+  CUDA_TRY(cudaStreamSynchronize(m->stream));          // a raycast in flight may still be writing the previous target
+  m->rt_dev = nullptr; m->rt_user = nullptr; m->rt_valid = false;
+  if (!out) return SE_B200_OK;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, out) != cudaSuccess) { cudaGetLastError(); return fail(SE_B200_ERR_ARG, "render target: not a CUDA-visible pointer"); }
+  void* dev = nullptr;
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) dev = out;
+  else if (a.type == cudaMemoryTypeHost && a.devicePointer) dev = a.devicePointer;
+  if (!dev) return fail(SE_B200_ERR_ARG, "render target must be device memory or page-locked (pinned) host memory");
+  m->rt_dev = (uchar4*)dev; m->rt_user = out;
   return SE_B200_OK;
 }
 

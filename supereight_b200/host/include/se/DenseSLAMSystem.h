@@ -111,6 +111,9 @@ class DenseSLAMSystem {
   // -- additions (not in the reference) ----------------------------------------------------------
   // vertex / normal maps of the last raycast (W*H*3 floats each), for callers that consume them
   void getVertexNormal(std::vector<float>& vertex, std::vector<float>& normal);
+  // extension (se_b200_set_render_target): raycasting() also renders the reuse-path image into `out` (device memory or
+  // page-locked host memory, W*H*4 bytes; nullptr turns it off); renderVolume(out, ...) with the same pointer then only waits
+  void setRenderTarget(unsigned char* out);
   // device time of the last run of a stage in ms (stands in for the TICK/TOCK samples, se_shared/timings.h)
   float stageMilliseconds(int stage);
   se_b200_map* handle() { return map_; }

@@ -215,6 +215,10 @@ void DenseSLAMSystem::getVertexNormal(std::vector<float>& vertex, std::vector<fl
   SE_CHECK(se_b200_download_vertex_normal(map_, vertex.data(), normal.data()), "getVertexNormal");
 }
 
+void DenseSLAMSystem::setRenderTarget(unsigned char* out) {
+  SE_CHECK(se_b200_set_render_target(map_, out), "setRenderTarget");
+}
+
 float DenseSLAMSystem::stageMilliseconds(int stage) {
   float ms = 0.f;
   SE_CHECK(se_b200_elapsed_ms(map_, stage, &ms), "stageMilliseconds");

@@ -397,7 +397,14 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
-inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) { a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = (void*)p; return cudaSuccess; }
+// every pointer is pageable host memory -- unless SIMT_HOST_IS_PINNED=1, which makes every pointer look page-locked and mapped
+// (alias = the pointer itself), so that the zero-copy paths of the library can be exercised on the fiber executor
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  const char* e = std::getenv("SIMT_HOST_IS_PINNED");
+  const bool pinned = e && e[0] == '1';
+  a->type = pinned ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered; a->device = 0;
+  a->devicePointer = pinned ? (void*)p : nullptr; a->hostPointer = (void*)p; return cudaSuccess;
+}
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
 template <class... KArgs, class... Args>

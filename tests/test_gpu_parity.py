@@ -431,6 +431,62 @@ def test_ragged_image_sizes_and_tiny_volume():
     assert np.array_equal(g2.nodes_sorted()[0], o2.nodes_sorted()[0])
 
 
+def _pinned_image(H, W):
+    """(array view, address, keep-alive) of a page-locked H x W x 4 byte buffer; on the fiber executor (no CUDA driver) a plain
+    numpy buffer, which tests/test_simt_emu.py makes look page-locked to the library (SIMT_HOST_IS_PINNED=1)"""
+    import os
+    if "simt" in os.environ.get("SE_B200_LIB", ""):
+        a = np.zeros((H, W, 4), np.uint8)
+        return a, a.ctypes.data, a
+    import torch
+    t = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+    return t.numpy(), t.data_ptr(), t
+
+
+@pytest.mark.parametrize("field,mu", [(SDF, 0.1), (OFUSION, 0.008)])
+def test_render_target_image_equals_render_volume(field, mu):
+    """se_b200_set_render_target: the raycast shades into the caller's page-locked buffer and renderVolume's reuse path then
+    launches nothing -- same image, same vertex / normal maps, one launch fewer per frame; a different view pose, a re-raycast
+    or another destination still render as usual, and clearing the target restores the plain path."""
+    from supereight_b200 import Map, SeB200Error, synth
+    dim, W, H = 4.8, 160, 120
+    k = scaled_k(W)
+    a, b = Map(field, 256, dim, W, H), Map(field, 256, dim, W, H)
+    img, ptr, keep = _pinned_image(H, W)
+    b.set_render_target(ptr)
+    gen = synth.planar_sweep if field == SDF else synth.box_room
+    kw = dict(noise_mm=2.0) if field == SDF else dict(n_frames=300)
+    for f in range(4):
+        d, pose = gen(f, dim, W, H, k, dropout=0.01, **kw)
+        for m_ in (a, b):
+            m_.preprocess(d); m_.integrate(pose, k, mu, f)
+        la, lb = a.launch_count(), b.launch_count()
+        a.raycast(pose, k, mu); b.raycast(pose, k, mu)
+        want = a.render_volume(pose, k, mu, 0.75 * mu, False)
+        b.render_volume_host_ptr(ptr, pose, k, mu, 0.75 * mu, False)
+        assert (a.launch_count() - la, b.launch_count() - lb) == (2, 1)
+        assert np.array_equal(img, want)
+        va, na = a.vertex_normal(); vb, nb = b.vertex_normal()
+        assert va.tobytes() == vb.tobytes() and na.tobytes() == nb.tobytes()
+    assert want[..., 0].max() > 0 and (na[..., 0] != -2.0).sum() > 0.2 * W * H          # a real image: rays hit
+    # another destination, another view, a re-raycast: rendered the usual way
+    assert np.array_equal(b.render_volume(pose, k, mu, 0.75 * mu, False), want)
+    moved = pose.copy(); moved[0, 3] += 0.05
+    lb = b.launch_count()
+    b.render_volume_host_ptr(ptr, moved, k, mu, 0.75 * mu, False)
+    assert b.launch_count() - lb == 1 and np.array_equal(img, a.render_volume(moved, k, mu, 0.75 * mu, False))
+    b.render_volume_host_ptr(ptr, moved, k, mu, 0.75 * mu, True)
+    assert np.array_equal(img, a.render_volume(moved, k, mu, 0.75 * mu, True))
+    # target off: the plain kernels again
+    b.set_render_target(None)
+    lb = b.launch_count()
+    b.raycast(pose, k, mu); b.render_volume_host_ptr(ptr, pose, k, mu, 0.75 * mu, False)
+    assert b.launch_count() - lb == 2 and np.array_equal(img, want)
+    if "simt" not in __import__("os").environ.get("SE_B200_LIB", ""):
+        with pytest.raises(SeB200Error, match="page-locked"):
+            b.set_render_target(np.zeros((H, W, 4), np.uint8).ctypes.data)       # pageable host memory is refused
+
+
 def test_host_calls_with_pinned_buffers_match_pageable_ones():
     """se_b200_render_volume_host writes a page-locked destination in place (no staging copy) and
     se_b200_preprocess_depth_host copies asynchronously from a page-locked source: same bytes as with pageable buffers"""

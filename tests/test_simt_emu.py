@@ -58,6 +58,12 @@ def test_gpu_parity_test_passes_on_the_fiber_executor(emu_lib, nodeid):
     run_pytest_on_emu(emu_lib, nodeid)
 
 
+def test_render_target_extension(emu_lib):
+    """se_b200_set_render_target (raycast + shading fused, image written to the caller's page-locked buffer): the executor's
+    cudaPointerGetAttributes reports every pointer as page-locked and mapped when SIMT_HOST_IS_PINNED=1"""
+    run_pytest_on_emu(emu_lib, "tests/test_gpu_parity.py::test_render_target_image_equals_render_volume", {"SIMT_HOST_IS_PINNED": "1"})
+
+
 def test_tree_descent_without_the_directories(emu_lib):
     """SE_B200_DISABLE_DIRECTORY=1: every fetch is the root-to-leaf descent, the allocation pass de-duplicates in the warp"""
     run_pytest_on_emu(emu_lib, "tests/test_gpu_parity.py::test_sdf_ratio2_preprocess_and_empty_frames", {"SE_B200_DISABLE_DIRECTORY": "1"})
