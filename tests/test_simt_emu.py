@@ -42,7 +42,7 @@ FAST_GPU_TESTS = [
     "tests/test_gpu_parity.py::test_sdf_camera_outside_and_partially_out_of_volume",
     "tests/test_gpu_parity.py::test_sdf_weight_saturation_property",
     "tests/test_gpu_parity.py::test_sdf_ieee_division_fallback_paths",
-    "tests/test_gpu_parity.py::test_ofusion_plain_operator_instantiation",
+    "tests/test_zz_extensions.py::test_ofusion_plain_operator_instantiation",
     "tests/test_gpu_parity.py::test_ragged_image_sizes_and_tiny_volume",
     "tests/test_gpu_parity.py::test_error_paths_and_render_track",
     "tests/test_gpu_parity.py::test_map_export_import_round_trip",
@@ -61,7 +61,7 @@ def test_gpu_parity_test_passes_on_the_fiber_executor(emu_lib, nodeid):
 def test_render_target_extension(emu_lib):
     """se_b200_set_render_target (raycast + shading fused, image written to the caller's page-locked buffer): the executor's
     cudaPointerGetAttributes reports every pointer as page-locked and mapped when SIMT_HOST_IS_PINNED=1"""
-    run_pytest_on_emu(emu_lib, "tests/test_gpu_parity.py::test_render_target_image_equals_render_volume", {"SIMT_HOST_IS_PINNED": "1"})
+    run_pytest_on_emu(emu_lib, "tests/test_zz_extensions.py::test_render_target_image_equals_render_volume", {"SIMT_HOST_IS_PINNED": "1"})
 
 
 def test_tree_descent_without_the_directories(emu_lib):
