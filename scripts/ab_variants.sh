@@ -25,6 +25,17 @@ run "" box_room_sdf2048 60
 for v in stage4 all; do run $PWD/ab_libs/$v.so box_room_sdf2048 60; done
 run "" box_room_ofusion1024 60
 run $PWD/ab_libs/ray.so box_room_ofusion1024 60
+# the render-target extension: e2e vs e2e_render_target, with 8x4 and with 32x1 pixel tiles
+for v in "" $PWD/ab_libs/t32.so; do
+  SE_B200_BENCH_RENDER_TARGET=1 SE_B200_LIB=$v timeout 300 python bench.py --steps 200 --warmup 5 --no-cpu-baseline 2>&1 | python -c "
+import sys, json
+for line in sys.stdin:
+    line = line.strip()
+    if line.startswith('{'):
+        d = json.loads(line); print('render target lib=[$v] value', d['value'], 'e2e', d['e2e'], 'e2e_render_target', d['e2e_render_target'])
+" >> $LOG 2>&1
+done
+(echo "== extension tests"; timeout 300 python -m pytest tests/test_zz_extensions.py -x -q -m gpu 2>&1 | tail -3) >> $LOG 2>&1
 for v in stage4 ray all; do
   (echo "== parity on $v"; SE_B200_LIB=$PWD/ab_libs/$v.so timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sdf_512_full or sdf_2048 or ieee_division or point_queries or ofusion_plane" 2>&1 | tail -3) >> $LOG 2>&1
 done

@@ -199,6 +199,16 @@ void make_bspline_lut(float lut[1000]) {
 // 0, or finite with magnitude in [2^-20, 2^20]
 bool normal_range(float v) { const float a = std::fabs(v); return v == 0.f || (a >= 0x1p-20f && a <= 0x1p20f); }
 
+// CTAs of the per-pixel ray kernels (tile_pixel in se_kernels.cuh: 8x4 pixel tiles per warp)
+int ray_tile_blocks(int W, int H, int threads) {
+#ifdef SE_RAY_TILE_32X1
+  const int tiles = ((W + 31) / 32) * H;
+#else
+  const int tiles = ((W + 7) / 8) * ((H + 3) / 4);
+#endif
+  const int warps_per_block = threads / 32;
+  return (tiles + warps_per_block - 1) / warps_per_block;
+}
 int pixel_tile_blocks(int W, int H, int threads) {
   const int tiles = ((W + 7) / 8) * ((H + 3) / 4);
   const int warps_per_block = threads / 32;
@@ -363,11 +373,11 @@ int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu, un
   m->rt_valid = false;
   if (m->rt_dev && !stats_dev) {
     const V3 light = v3(pose[3], pose[7], pose[11]);           // the reuse path's light: view pose == raycast pose
-    launch_pdl(k_raycast_shade<V>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, light, m->rt_dev);
+    launch_pdl(k_raycast_shade<V>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, light, m->rt_dev);
     m->rt_light[0] = pose[3]; m->rt_light[1] = pose[7]; m->rt_light[2] = pose[11];
     m->rt_valid = true;
-  } else if (stats_dev) launch_pdl(k_raycast<V, true>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
-  else launch_pdl(k_raycast<V, false>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
+  } else if (stats_dev) launch_pdl(k_raycast<V, true>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
+  else launch_pdl(k_raycast<V, false>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RAYCAST);
   return SE_B200_OK;
@@ -384,7 +394,7 @@ int render_volume_impl(se_b200_map* m, uchar4* out_dev, const float* view_pose, 
   const RaycastParams rp = make_raycast_params(m, view_pose, k, mu, kFarPlane * 2.0f, largestep, 0);   // DenseSLAMSystem.cpp:283-288
   const V3 light = v3(view_pose[3], view_pose[7], view_pose[11]);
   stage_begin(m, SE_B200_STAGE_RENDER);
-  if (reraycast) launch_pdl(k_render_volume<V>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
+  if (reraycast) launch_pdl(k_render_volume<V>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
   else launch_pdl(k_render_shade, (m->W * m->H + 255) / 256, 256, 0, m->stream, m->d_vertex, m->d_normal, light, m->W * m->H, out_dev);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RENDER);

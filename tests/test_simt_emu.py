@@ -79,6 +79,9 @@ EXPERIMENTS = [
     (("-DSE_GRAD_NBHD", "-DSE_RAY_UNIFORMS"), "_ray", ["tests/test_gpu_parity.py::test_point_queries_match_oracle_all_gather_cases",
                                                        "tests/test_gpu_parity.py::test_sdf_camera_outside_and_partially_out_of_volume",
                                                        "tests/test_gpu_parity.py::test_sdf_negative_fy_camera"]),
+    # ray kernels with 32x1 pixel tiles per warp instead of 8x4 (se_kernels.cuh tile_pixel)
+    (("-DSE_RAY_TILE_32X1",), "_t32", ["tests/test_gpu_parity.py::test_ragged_image_sizes_and_tiny_volume",
+                                       "tests/test_gpu_parity.py::test_sdf_camera_outside_and_partially_out_of_volume"]),
 ]
 
 
