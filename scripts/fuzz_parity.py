@@ -1,0 +1,153 @@
+"""Randomised parity check of the product kernels against the oracle: random volumes, cameras (inside and outside the volume,
+rolled, negative fy), depth images (planes, blobs, noise, drop-outs, saturated and 1 mm samples) and short sequences; after
+every scenario the block set, voxel and node values, vertex / normal maps and both renderings are compared -- bit for bit
+for the SDF field, to the test suite's tolerances for OFusion.
+  python scripts/fuzz_parity.py [n_scenarios] [first_seed]
+Runs wherever the library runs: on a B200, or in the build container on the fiber executor
+(SE_B200_LIB=tests/simt_emu/_build/libse_b200_simt.so; ~1 s per scenario).  Prints one line per failing scenario and a summary;
+exit status 1 if anything differed."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib  # noqa: E402
+from oracle_lib import OFUSION, SDF, Oracle  # noqa: E402
+from parity_utils import compare_blocks, compare_images, compare_nodes  # noqa: E402
+
+from supereight_b200 import Map, synth  # noqa: E402
+
+
+def random_pose(rng, dim):
+    mode = rng.integers(4)
+    if mode == 0:        # inside, looking at a random point inside
+        eye = rng.uniform(0.05, 0.95, 3) * dim
+    elif mode == 1:      # outside the volume, looking in
+        eye = rng.uniform(-0.6, 1.6, 3) * dim
+    elif mode == 2:      # on a face / edge of the volume
+        eye = rng.uniform(0.0, 1.0, 3) * dim
+        eye[rng.integers(3)] = rng.choice([0.0, dim])
+    else:                # axis-aligned view (zero direction components exercise the epsilon clamp of the ray set-up)
+        eye = rng.uniform(0.1, 0.9, 3) * dim
+        tgt = eye.copy(); tgt[rng.integers(3)] += rng.choice([-1.0, 1.0]) * dim
+        with np.errstate(invalid="ignore", divide="ignore"):
+            pose = synth.look_at_pose(eye, tgt, 0.0)              # looking straight along y has no defined "up": NaN
+        if not np.all(np.isfinite(pose)):
+            pose = synth.yaw_pose(*eye, float(rng.choice([0.0, np.pi / 2, np.pi])))
+        return pose
+    tgt = rng.uniform(0.2, 0.8, 3) * dim
+    if np.linalg.norm(tgt - eye) < 1e-3:
+        tgt = tgt + 0.1 * dim
+    pose = synth.look_at_pose(eye, tgt, rng.uniform(-np.pi, np.pi))
+    if not np.all(np.isfinite(pose)):
+        pose = synth.yaw_pose(*(rng.uniform(0.2, 0.8, 3) * dim), rng.uniform(-3, 3))
+    return pose
+
+
+def random_depth(rng, W, H, dim):
+    kind = rng.integers(4)
+    u, v = np.meshgrid(np.arange(W), np.arange(H))
+    if kind == 0:        # tilted plane
+        d = rng.uniform(0.3, 1.2) * dim * (1 + rng.uniform(-0.5, 0.5) * (u / W - 0.5) + rng.uniform(-0.5, 0.5) * (v / H - 0.5))
+    elif kind == 1:      # blobs on a background
+        d = np.full((H, W), rng.uniform(0.5, 1.5) * dim)
+        for _ in range(rng.integers(1, 5)):
+            cx, cy, r = rng.uniform(0, W), rng.uniform(0, H), rng.uniform(3, W / 3)
+            d[(u - cx) ** 2 + (v - cy) ** 2 < r * r] = rng.uniform(0.1, 1.0) * dim
+    elif kind == 2:      # white noise between near and far
+        d = rng.uniform(0.05, 1.5, (H, W)) * dim
+    else:                # steps
+        d = (1 + (u // max(W // 6, 1)) % 3) * rng.uniform(0.15, 0.4) * dim
+    d = d * 1000.0 + rng.normal(0, rng.choice([0.0, 2.0, 20.0]), (H, W))
+    out = np.clip(np.rint(d), 0, 65535).astype(np.uint16)
+    out[rng.random((H, W)) < rng.choice([0.0, 0.02, 0.3])] = 0
+    if rng.random() < 0.3:
+        out[rng.random((H, W)) < 0.02] = 65535        # saturated samples
+    if rng.random() < 0.3:
+        out[rng.random((H, W)) < 0.02] = 1            # 1 mm samples
+    return np.ascontiguousarray(out)
+
+
+def scenario(seed):
+    rng = np.random.default_rng(seed)
+    field = int(rng.integers(2))
+    size = int(rng.choice([16, 32, 64, 128, 256]))
+    dim = float(rng.choice([0.5, 1.0, 2.0, 4.8, 10.0]))
+    W, H = int(rng.integers(9, 97)), int(rng.integers(5, 73))
+    f = rng.uniform(0.6, 2.0) * W
+    k = (float(f), float(f * rng.choice([1.0, -1.0, 0.9])), float(W / 2 + rng.uniform(-5, 5)), float(H / 2 + rng.uniform(-5, 5)))
+    mu = float(rng.choice([0.1, 0.05, 0.02]) if field == SDF else rng.choice([0.008, 0.02]))
+    if field == SDF and 2 * mu / (dim / size) > 90:
+        mu = 40 * dim / size                              # keeps the band below the per-ray block list (100 samples)
+    g, o = Map(field, size, dim, W, H), Oracle(field, size, dim, W, H)
+    o.set_counting(True)
+    reserved = (size // 8) * W * H             # DenseSLAMSystem.cpp:212-215
+    n_frames = int(rng.integers(1, 5))
+    pose = None
+    for fr in range(n_frames):
+        if pose is None or rng.random() < 0.5:
+            pose = random_pose(rng, dim)
+        d = random_depth(rng, W, H, dim)
+        o.reset_counters()
+        o.preprocess(d); o.integrate(pose, k, mu, fr)
+        if o.counters()["n_keys_raw"] >= reserved:
+            # The reference stops recording requests when its reserved list is full (alloc_impl.hpp:103-106); which requests
+            # are lost depends on the OpenMP interleaving, so there is no reference answer.  (The library has no such list.)
+            return None
+        g.preprocess(d); g.integrate(pose, k, mu, fr)
+    problems = []
+    cb = compare_blocks(g, o)
+    if not cb["keys_equal"]:
+        return [f"block sets differ {cb}"]
+    if not cb["coords_equal"] or cb["active_mismatch"]:
+        problems.append(f"block coords/active {cb}")
+    cn = compare_nodes(g, o)
+    if not (cn["codes_equal"] and cn.get("side_equal") and cn.get("mask_equal")):
+        problems.append(f"nodes {cn}")
+    if field == SDF:
+        if cb["x_bit_mismatch"] or cb["y_mismatch"] or cn.get("x_bit_mismatch") or cn.get("y_mismatch"):
+            problems.append(f"SDF values {cb} {cn}")
+    else:
+        # occupancies: the test suite's bar (tests/test_gpu_parity.py assert_ofusion_parity: rtol 1e-4, atol 1e-5) -- the oracle's
+        # log2f (glibc) and the device's correctly rounded log2 differ by an ulp on some arguments, and updates accumulate
+        if cb["y_mismatch"] or cb["x_max_abs"] > 1e-5 + 1e-4 * 1000.0 or (cb["x_max_rel"] > 1e-4 and cb["x_max_abs"] > 1e-5):
+            problems.append(f"OFusion values {cb}")
+        if cn.get("y_mismatch") or (cn.get("x_max_rel", 0) > 1e-4):
+            problems.append(f"OFusion node values {cn}")
+    view = pose if rng.random() < 0.7 else random_pose(rng, dim)
+    o.raycast(view, k, mu); g.raycast(view, k, mu)
+    gv, gn = g.vertex_normal()
+    ci = compare_images(gv, gn, o.vertex(), o.normal())
+    if field == SDF:
+        if ci["hit_mask_mismatch"] or ci["vertex_bit_mismatch"] or ci["normal_bit_mismatch"]:
+            problems.append(f"raycast {ci}")
+        for rer in (False, True):
+            if not np.array_equal(g.render_volume(view, k, mu, 0.75 * mu, rer), o.render_volume(view, k, mu, 0.75 * mu, rer)):
+                problems.append(f"render_volume(reraycast={rer}) differs")
+    else:
+        if ci["hit_mask_mismatch"] > 0.01 * W * H + 2:
+            problems.append(f"OFusion raycast {ci}")
+    return problems
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    oracle_lib.build()
+    bad = skipped = 0
+    for s in range(first, first + n):
+        try:
+            p = scenario(s)
+        except Exception as e:                       # an error return of the library is a finding too
+            p = [f"{type(e).__name__}: {e}"]
+        if p is None:
+            skipped += 1
+        elif p:
+            bad += 1
+            print(f"seed {s}: " + " | ".join(p)[:1500], flush=True)
+    print(f"{n} scenarios (seeds {first}..{first + n - 1}): {n - bad - skipped} identical, {bad} with differences, "
+          f"{skipped} skipped (the reference's allocation list overflowed: no defined answer)")
+    sys.exit(1 if bad else 0)

@@ -64,6 +64,17 @@ def test_render_target_extension(emu_lib):
     run_pytest_on_emu(emu_lib, "tests/test_zz_extensions.py::test_render_target_image_equals_render_volume", {"SIMT_HOST_IS_PINNED": "1"})
 
 
+def test_randomised_parity_scenarios(emu_lib):
+    """scripts/fuzz_parity.py: random volumes, cameras (inside / outside / on the faces of the volume, axis-aligned, negative
+    fy), depth images and short sequences through the product kernels and the oracle -- a fixed batch of seeds here, any
+    number by hand or on the device (150 more were run when it was written: no difference)."""
+    env = dict(os.environ, SE_B200_LIB=emu_lib)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_parity.py"), "16", "1000"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " 0 with differences" in r.stdout, r.stdout[-1000:]
+
+
 def test_tree_descent_without_the_directories(emu_lib):
     """SE_B200_DISABLE_DIRECTORY=1: every fetch is the root-to-leaf descent, the allocation pass de-duplicates in the warp"""
     run_pytest_on_emu(emu_lib, "tests/test_gpu_parity.py::test_sdf_ratio2_preprocess_and_empty_frames", {"SE_B200_DISABLE_DIRECTORY": "1"})
