@@ -18,7 +18,10 @@ import oracle_lib  # noqa: E402
 from oracle_lib import OFUSION, SDF, Oracle  # noqa: E402
 from parity_utils import compare_blocks, compare_images, compare_nodes  # noqa: E402
 
+import mc_table_ref  # noqa: E402  (tests/: independent generator of the marching-cubes case table)
 from supereight_b200 import Map, synth  # noqa: E402
+
+MC_TABLE = mc_table_ref.table()
 
 
 def random_pose(rng, dim):
@@ -127,6 +130,20 @@ def scenario(seed):
         for rer in (False, True):
             if not np.array_equal(g.render_volume(view, k, mu, 0.75 * mu, rer), o.render_volume(view, k, mu, 0.75 * mu, rer)):
                 problems.append(f"render_volume(reraycast={rer}) differs")
+        # point queries at random positions (also on and beyond the volume's faces): get / interp / grad, bit for bit
+        pos = np.concatenate([rng.uniform(-2, size + 2, (200, 3)), rng.uniform(0, size, (200, 3))]).astype(np.float32)
+        gi, gg = g.query_interp(pos), g.query_grad(pos)
+        oi = np.array([o.interp(float(q[0]), float(q[1]), float(q[2])) for q in pos], np.float32)
+        og = np.array([o.grad(float(q[0]), float(q[1]), float(q[2])) for q in pos], np.float32)
+        inside = np.all((pos >= 0) & (pos < size - 1), axis=1)      # interp reads out of bounds beyond the faces in the reference
+        if not np.array_equal(gi.view(np.uint32)[inside], oi.view(np.uint32)[inside]):
+            problems.append("interp differs")
+        if not np.array_equal(gg.view(np.uint32), og.view(np.uint32)):
+            problems.append("grad differs")
+        # N4: the mesh, triangle by triangle
+        got, want = g.mesh(), o.marching_cube(MC_TABLE)
+        if got.shape != want.shape or not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
+            problems.append(f"mesh differs ({got.shape} vs {want.shape})")
     else:
         if ci["hit_mask_mismatch"] > 0.01 * W * H + 2:
             problems.append(f"OFusion raycast {ci}")
