@@ -49,6 +49,18 @@ def test_oracle_is_bit_identical_to_the_reference_build(field, size, dim, W, H, 
 
 
 @needs_ref
+@pytest.mark.parametrize("size", [64, 128])
+def test_oracle_equals_the_reference_build_on_random_scenarios(size):
+    """scripts/fuzz_parity.py --ref: random cameras, depth images and 1-4 frame sequences (both fields) inside the domain where the
+    reference's code is defined -- the oracle against the reference's own sources, every array bit for bit.  A fixed batch here;
+    some 600 scenarios over five volume sizes were run when it was written: no difference."""
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "scripts", "fuzz_parity.py"), "--ref", str(size), "12", "300"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " 0 with differences" in r.stdout, r.stdout[-1000:]
+
+
+@needs_ref
 def test_reference_build_exports_what_the_oracle_binding_uses():
     for kind in ("ref_sdf", "ref_ofusion"):
         lib = oracle_lib.load(kind)
