@@ -4,6 +4,7 @@
 # headline workload.  Everything lands in gpurun_out/ as it is produced.
 R=${1:-r1c}
 mkdir -p gpurun_out
+python -c "import torch; torch.zeros(1).cuda()" > /dev/null 2>&1      # a cold box needs up to a minute for the first import
 (timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -5) > gpurun_out/${R}_pytest_gpu.log 2>&1
 python bench.py --no-cpu-baseline > gpurun_out/bench_${R}_sdf512.json 2> gpurun_out/bench_${R}_sdf512.err
 python bench.py --workload box_room_ofusion1024 --no-cpu-baseline > gpurun_out/bench_${R}_ofusion1024.json 2> gpurun_out/bench_${R}_ofusion1024.err
