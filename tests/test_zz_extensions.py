@@ -1,6 +1,6 @@
-"""GPU tests of what this round added last and could not yet run on the device -- the render-target extension and the
-OFusion integrate's default instantiation against its plain-operator twin -- kept in a file that pytest runs after the
-parity files (it orders files by name), so that `-x` never lets them hide an established test."""
+"""GPU tests of what this round added last and could not yet run on the device -- the render-target extension, the OFusion
+integrate's default instantiation against its plain-operator twin, and a batch of randomised parity scenarios -- kept in a
+file that pytest runs after the parity files (it orders files by name), so that `-x` never lets them hide an established test."""
 import numpy as np
 import pytest
 
@@ -90,3 +90,17 @@ def test_ofusion_plain_operator_instantiation(monkeypatch):
         assert np.array_equal(d0["y"], d1["y"])
         assert np.count_nonzero(d0["x"].view(np.uint32) != d1["x"].view(np.uint32)) < 1e-3 * d0["x"].size
         np.testing.assert_allclose(d0["x"], d1["x"], rtol=REL_TOL, atol=1e-5)
+
+
+def test_randomised_parity_scenarios_on_the_device():
+    """scripts/fuzz_parity.py through whatever library the tests run on: 60 random scenarios (volumes 16^3..256^3, cameras inside /
+    outside / on the faces of the volume, axis-aligned views, negative fy, noisy / saturated / 1 mm depth, 1-4 frames), each compared
+    with the oracle -- block set, voxel and node values, vertex / normal maps, both renderings, interp / grad queries, the mesh."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "60", "9000"], cwd=root,
+                       capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " 0 with differences" in r.stdout, r.stdout[-1000:]
