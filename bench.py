@@ -295,6 +295,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
     m.close()
 
     m = new_map()
+    m.set_stage_timing(True)
     for f in range(warmup):
         flush.zero_(); step_resident(f)
     barrier()

@@ -19,6 +19,7 @@
 #ifndef SE_B200_H
 #define SE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -36,6 +37,13 @@ enum {
   SE_B200_ERR_CUDA = -2,      /* CUDA runtime error, or no device */
   SE_B200_ERR_POOL = -3       /* node/block pool exhausted (reference: allocation list silently truncated, kfusion/alloc_impl.hpp:103-106) */
 };
+/* SE_B200_ERR_POOL and the per-frame path.  A pool runs out on the device, in the middle of se_b200_integrate's allocation
+ * pass, and the per-frame calls never wait for the device: the octants that did not fit are dropped for that frame (they are
+ * requested again by the next one), the frame's integrate kernel hands the error bits to the host through a word of
+ * mapped page-locked memory, and the NEXT se_b200_integrate / se_b200_raycast (normally one frame later; at the latest
+ * after a synchronising call) returns SE_B200_ERR_POOL once and clears the condition.  se_b200_block_count,
+ * se_b200_node_count, se_b200_counters and the map import calls synchronise and report it at once.  Re-create the map with
+ * larger max_blocks / max_nodes (se_b200_download_* + se_b200_upload_* carry the content over). */
 
 /* voxel payload layouts, identical to the reference structs (volume_traits.hpp:41-44, 62-65) */
 typedef struct { float x; float y; } se_b200_sdf_voxel;                 /* tsdf in [-1,1], weight */
@@ -63,8 +71,21 @@ int se_b200_sync(se_b200_map* map);
 /* ---- a1: mm2metersKernel (se_denseslam/src/preprocessing.cpp:161-188) -------------------
  * depth_mm is inW x inH uint16 millimetres; the result is the W x H float depth (metres) that
  * integration and renderDepth read.  inW/W == inH/H must be a whole ratio.
- * _host: pointer to host memory (copied inside the call, asynchronously if it is pinned);
- * _device: pointer to device memory already holding the frame. */
+ * _host: pointer to host memory (copied to a staging buffer in HBM inside the call, asynchronously if it is page-locked);
+ * _device: pointer to device memory already holding the frame.
+ * The conversion itself is deferred: the allocation kernel of the next se_b200_integrate reads every pixel exactly once
+ * anyway and converts it there (any other consumer of the float image -- se_b200_filter_depth, se_b200_render_depth_host,
+ * se_b200_device_image(0) -- triggers a conversion kernel first); results are those of the eager kernel, bit for bit.
+ * Buffer lifetime.  _host with PAGE-LOCKED memory: the copy is asynchronous -- do not modify depth_mm until a
+ * synchronising call (se_b200_sync, any call that returns data to host memory) has returned; pageable memory is staged
+ * before the call returns.  _device: depth_mm_dev is READ LATER, in stream order, by that next consumer -- keep it valid
+ * and unchanged until the work of the se_b200_integrate (or other consumer) that follows has been enqueued AND anything
+ * you then do to the buffer is ordered after the map's stream.
+ * se_b200_register_host_buffer page-locks (cudaHostRegister) a caller-owned buffer -- the reference application malloc()s its
+ * depth and RGBA buffers (se_apps/src/benchmark.cpp:90-97), which makes every transfer a staged, synchronous copy; registering
+ * them once makes the _host calls above and below asynchronous / zero-copy.  Unregister before freeing the memory. */
+int se_b200_register_host_buffer(void* ptr, size_t bytes);
+int se_b200_unregister_host_buffer(void* ptr);
 int se_b200_preprocess_depth_host(se_b200_map* map, const uint16_t* depth_mm, int inW, int inH);
 int se_b200_preprocess_depth_device(se_b200_map* map, const uint16_t* depth_mm_dev, int inW, int inH);
 /* test/IO helper: set the float depth image directly (W*H floats, host memory) */
@@ -190,7 +211,9 @@ int se_b200_query_rays(se_b200_map* map, const float* origin_dir, int n, float n
 enum { SE_B200_STAGE_PREPROCESS = 0, SE_B200_STAGE_ALLOC = 1, SE_B200_STAGE_FUSE = 2, SE_B200_STAGE_RAYCAST = 3,
        SE_B200_STAGE_RENDER = 4, SE_B200_NUM_STAGES = 5 };
 int se_b200_elapsed_ms(se_b200_map* map, int stage, float* ms);
-/* the per-stage event pairs are recorded by default; 0 turns them off (ten event records less per frame) */
+/* per-stage CUDA event pairs for se_b200_elapsed_ms.  OFF by default: an event record between two kernel launches breaks the
+ * programmatic-dependent-launch edge between them (every per-frame kernel overlaps its prologue with its predecessor's tail),
+ * so timing costs ~10 % of the frame; enable != 0 turns the events on (benchmarks, DenseSLAMSystem::stageMilliseconds). */
 int se_b200_set_stage_timing(se_b200_map* map, int enable);
 /* counters of the last integrate: [0] nodes, [1] blocks, [2] active blocks, [3] error bits,
  * [4] blocks before the frame, [5] nodes before the frame, [6] octant requests (OFusion) */

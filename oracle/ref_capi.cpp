@@ -31,10 +31,11 @@ struct Handle {
   std::vector<uint16_t> last_depth;
   int last_w = 0, last_h = 0;
   Eigen::Matrix4f view;                // storage for viewPose_
+  se::Octree<FieldType>* tree = nullptr;   // seo_load_map: a stand-alone octree read by the reference's Octree::load (no pipeline around it)
 };
 Eigen::Matrix4f to_m4(const float* p) { Eigen::Matrix4f m; for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) m(r, c) = p[4 * r + c]; return m; }
 Eigen::Vector4f to_k(const float* k) { return Eigen::Vector4f(k[0], k[1], k[2], k[3]); }
-se::Octree<FieldType>& map_of(Handle* h) { return *h->sys->volume_._map_index; }
+se::Octree<FieldType>& map_of(Handle* h) { return h->tree ? *h->tree : *h->sys->volume_._map_index; }
 auto select_x = [](const Voxel& v) { return v.x; };
 }  // namespace
 
@@ -53,7 +54,23 @@ void* seo_create(int field, int size, float dim, int W, int H) {
   h->sys = new DenseSLAMSystem(Eigen::Vector2i(W, H), Eigen::Vector3i::Constant(size), Eigen::Vector3f::Constant(dim), init, pyramid, config);
   return h;
 }
-void seo_destroy(void* hh) { Handle* h = (Handle*)hh; delete h->sys; delete h; }
+void seo_destroy(void* hh) { Handle* h = (Handle*)hh; delete h->sys; delete h->tree; delete h; }
+
+// ---- N3: the reference's own map file writer / reader (octree.hpp:897-950, io/se_serialise.hpp:54-99) --------------
+int seo_save_map(void* hh, const char* path) { map_of((Handle*)hh).save(path); return 0; }
+// Octree::load into a fresh, stand-alone octree; the handle answers the block / node / point queries below.
+// NB the reference reads the file's float `dim` into an int (octree.hpp:921-923), so the loaded tree's dim_ is the float's
+// bit pattern converted to float; `dim_fix` > 0 repairs it (private member, this file is built with -fno-access-control)
+// so that metric queries on the loaded tree are meaningful.
+void* seo_load_map(const char* path, float dim_fix) {
+  Handle* h = new Handle;
+  h->tree = new se::Octree<FieldType>;
+  h->tree->load(path);
+  if (dim_fix > 0.f) h->tree->dim_ = dim_fix;
+  return h;
+}
+int seo_map_size(void* hh) { return map_of((Handle*)hh).size(); }
+float seo_map_dim(void* hh) { return map_of((Handle*)hh).dim(); }
 void seo_set_omp_threads(int n) { omp_set_num_threads(n); }
 
 // mm2metersKernel exit(1)s on a bad ratio (preprocessing.cpp:166-176): report it instead, as the oracle does

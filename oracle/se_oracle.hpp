@@ -760,8 +760,8 @@ static inline void bilateral_filter(std::vector<float>& out, const std::vector<f
     }
 }
 // preprocessing.cpp:190-226 (r = 1, e_d = 3 * e_delta at the call site, DenseSLAMSystem.cpp:151)
-static inline void half_sample_robust(std::vector<float>& out, const std::vector<float>& in, int outW, int outH, float e_d, int r) {
-  const int inW = outW * 2;
+// inW = in.width(): the parent level's own row stride (2 outW + 1 when its width is odd); the clamp stays at 2 out - 1 (:214-216)
+static inline void half_sample_robust(std::vector<float>& out, const std::vector<float>& in, int outW, int outH, int inW, float e_d, int r) {
 #pragma omp parallel for
   for (int y = 0; y < outH; ++y)
     for (int x = 0; x < outW; ++x) {
@@ -1270,7 +1270,7 @@ template <class F> struct Pipeline {
   // vertex/normal maps (raycast_pose_).  iterations[level] as Configuration::pyramid.
   bool tracking(M4& pose, const M4& raycast_pose, const float k[4], float icp_threshold, const int* iterations, int levels) {
     ensure_pyramid(levels);
-    for (int i = 1; i < levels; ++i) half_sample_robust(scaled_depth[i], scaled_depth[i - 1], W >> i, H >> i, kEDelta * 3, 1);
+    for (int i = 1; i < levels; ++i) half_sample_robust(scaled_depth[i], scaled_depth[i - 1], W >> i, H >> i, W >> (i - 1), kEDelta * 3, 1);
     for (int i = 0; i < levels; ++i) {
       const float ks[4] = { k[0] / (float)(1 << i), k[1] / (float)(1 << i), k[2] / (float)(1 << i), k[3] / (float)(1 << i) };
       depth2vertex(input_vertex[i], scaled_depth[i], W >> i, H >> i, inverse_camera_matrix(ks));

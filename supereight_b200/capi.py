@@ -27,6 +27,7 @@ EXPORTS = (
     "se_b200_query_grad", "se_b200_set_voxels", "se_b200_query_rays", "se_b200_elapsed_ms", "se_b200_set_stage_timing", "se_b200_counters",
     "se_b200_launch_count", "se_b200_device_image", "se_b200_extract_mesh", "se_b200_download_mesh", "se_b200_mc_table",
     "se_b200_preprocess_depth_host_async", "se_b200_render_volume_host_async", "se_b200_set_render_target",
+    "se_b200_register_host_buffer", "se_b200_unregister_host_buffer",
 )
 
 
@@ -69,6 +70,9 @@ def load_library():
     lib.se_b200_render_volume_device.argtypes = [vp, vp, vp, vp, f32, f32, i32]
     lib.se_b200_render_depth_host.argtypes = [vp, vp]
     lib.se_b200_set_render_target.argtypes = [vp, vp]
+    if hasattr(lib, "se_b200_register_host_buffer"):       # (absent from older builds loaded through SE_B200_LIB for A/B runs)
+        lib.se_b200_register_host_buffer.argtypes = [vp, C.c_size_t]
+        lib.se_b200_unregister_host_buffer.argtypes = [vp]
     lib.se_b200_render_track_host.argtypes = [vp, vp, vp, i32]
     lib.se_b200_filter_depth.argtypes = [vp, i32, i32]
     lib.se_b200_track.argtypes = [vp, vp, vp, vp, f32, vp, i32, C.POINTER(i32)]

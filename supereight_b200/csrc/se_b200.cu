@@ -51,6 +51,7 @@ struct Pools {
   int* counters = nullptr;
   int* dir = nullptr;
   int* ndir = nullptr;
+  unsigned char* cmask = nullptr;
 };
 
 }  // namespace
@@ -69,7 +70,14 @@ struct se_b200_map {
   uchar4* d_rgba = nullptr;
   unsigned short* d_depth_mm = nullptr;
   size_t depth_mm_capacity = 0;
+  // The millimetre image of the last preprocess call that nobody has converted yet (mm2meters is deferred to the
+  // allocation kernel, which reads every pixel exactly once anyway; resolve_depth() converts on demand for the other
+  // consumers of the float image).  pending_slot: the async-upload staging buffer it lives in, or -1.
+  const unsigned short* pending_mm = nullptr;
+  int pending_inW = 0, pending_ratio = 1, pending_slot = -1;
   int* d_active_list = nullptr;
+  int* d_miss = nullptr;                  // SDF: directory cells of the blocks the allocation pass found missing (MissList)
+  int miss_capacity = 0;
   unsigned long long* d_requests = nullptr;
   float* d_logodds = nullptr;             // OFusion: log-odds increment per (bspline slot(t), slot(t-3)) pair (k_fill_logodds)
   int* d_track = nullptr;
@@ -89,6 +97,8 @@ struct se_b200_map {
   float* d_mesh = nullptr;               // 9 floats per triangle
   long long mesh_triangles = 0, mesh_capacity = 0;
   int* h_counters = nullptr;              // pinned
+  int* h_status = nullptr;                // pinned + mapped: [0] = the allocation pass's error bits, written by the integrate kernel
+  int* d_status = nullptr;                // its device alias
   cudaStream_t stream = nullptr, own_stream = nullptr;
   // overlapped host I/O (se_b200_*_host_async): the copy engines run on their own streams, double-buffered in HBM, tied
   // to the kernel stream by events, so frame N+1's upload and frame N's download overlap the kernels
@@ -113,7 +123,7 @@ struct se_b200_map {
   long long launches = 0;
   int grid_integrate = 0;
   int parity = 0;
-  bool stage_timing = true;
+  bool stage_timing = false;            // per-stage event pairs (se_b200_set_stage_timing): off by default -- an event between two launches breaks their programmatic-dependent-launch edge
 
   template <class V> MapView<V> view() const {
     MapView<V> v;
@@ -126,6 +136,7 @@ struct se_b200_map {
     v.counters = p.counters;
     v.dir = p.dir; v.dir_dim = size / kBlockSide;
     v.ndir = p.ndir;
+    v.cmask = p.cmask;
     return v;
   }
 };
@@ -200,15 +211,6 @@ void make_bspline_lut(float lut[1000]) {
 bool normal_range(float v) { const float a = std::fabs(v); return v == 0.f || (a >= 0x1p-20f && a <= 0x1p20f); }
 
 // CTAs of the per-pixel ray kernels (tile_pixel in se_kernels.cuh: 8x4 pixel tiles per warp)
-int ray_tile_blocks(int W, int H, int threads) {
-#ifdef SE_RAY_TILE_32X1
-  const int tiles = ((W + 31) / 32) * H;
-#else
-  const int tiles = ((W + 7) / 8) * ((H + 3) / 4);
-#endif
-  const int warps_per_block = threads / 32;
-  return (tiles + warps_per_block - 1) / warps_per_block;
-}
 int pixel_tile_blocks(int W, int H, int threads) {
   const int tiles = ((W + 7) / 8) * ((H + 3) / 4);
   const int warps_per_block = threads / 32;
@@ -240,6 +242,13 @@ int create_pools(se_b200_map* m) {
       CUDA_TRY(cudaMalloc(&m->p.ndir, ncells * sizeof(int)));
       CUDA_TRY(cudaMemsetAsync(m->p.ndir, 0xFF, ncells * sizeof(int), m->stream));
     }
+    // children masks by heap index for the levels 0 .. leaves_level-1 (MapView::cmask): 37 KB at 512^3, 2.4 MB at 2048^3,
+    // 153 MB at 8192^3 (heap indices stay below 2^31 up to there)
+    if (m->leaves_level <= 10) {
+      const size_t nmask = ((size_t)heap_level_offset(m->leaves_level) + 3) & ~(size_t)3;
+      CUDA_TRY(cudaMalloc(&m->p.cmask, nmask));
+      CUDA_TRY(cudaMemsetAsync(m->p.cmask, 0, nmask, m->stream));
+    }
   }
   CUDA_TRY(cudaMemsetAsync(m->p.node_child, 0xFF, nn * 8 * sizeof(int), m->stream));      // kEmpty
   CUDA_TRY(cudaMemsetAsync(m->p.node_code, 0, nn * sizeof(unsigned long long), m->stream));
@@ -269,8 +278,38 @@ int fetch_counters(se_b200_map* m) {
   return SE_B200_OK;
 }
 
+int check_pool_error(se_b200_map* m);
+
+// The allocation pass cannot fail synchronously (a pool runs out on the device, in the middle of a frame): find_or_create
+// sets an error bit, the frame's integrate kernel copies the bits to a word of mapped page-locked memory, and the next
+// stage call that sees them reports SE_B200_ERR_POOL -- without a device synchronisation on the per-frame path.  Reporting
+// clears the bits (device and host side); the octants that did not fit are lost for that frame and requested again by
+// the next one.
+int report_pool_error(se_b200_map* m) {
+  const int err = *(volatile int*)m->h_status;
+  if (!err) return SE_B200_OK;
+  m->h_status[0] = 0;
+  CUDA_TRY(cudaMemsetAsync(m->p.counters + kCntError, 0, sizeof(int), m->stream));
+  m->h_counters[kCntError] = err;
+  const int r = check_pool_error(m);
+  m->h_counters[kCntError] = 0;
+  return r;
+}
+
+// the float depth image, for its consumers other than the allocation kernels (which convert the pending millimetre
+// image themselves)
+int resolve_depth(se_b200_map* m) {
+  if (!m->pending_mm) return SE_B200_OK;
+  dim3 block(32, 8), grid((m->W + 31) / 32, (m->H + 7) / 8);
+  launch_pdl(k_mm2meters, grid, block, 0, m->stream, m->d_depth, m->pending_mm, m->W, m->H, m->pending_inW, m->pending_ratio);
+  if (m->pending_slot >= 0) { cudaEventRecord(m->aio.consumed[m->pending_slot], m->stream); m->aio.consumed_valid[m->pending_slot] = true; }
+  m->pending_mm = nullptr; m->pending_slot = -1;
+  return check_launch(m);
+}
+
 template <class V>
 int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu, unsigned frame) {
+  if (int r = report_pool_error(m)) return r;
   const M4 pose = to_m4(pose_p);
   const float voxelsize = m->dim / (float)m->size;                       // DenseSLAMSystem.cpp:211
   const float band = FieldTraits<V>::is_sdf ? 2 * mu : 6 * mu;           // :223, :228
@@ -284,6 +323,24 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   ap.band = band;
   ap.numSteps = (int)std::ceil(band * ap.inverseVoxelSize);
   ap.W = m->W; ap.H = m->H;
+  bool alloc_fast = !getenv("SE_B200_IEEE_DIV") && normal_range(band) && band > 0.f && ap.numSteps >= 1;
+  for (int i = 0; i < 12 && alloc_fast; ++i) alloc_fast = normal_range(ap.kPose.m[i]);
+  ap.fast = alloc_fast ? 1 : 0;
+  MissList miss;
+  miss.cells = nullptr; miss.capacity = 0;
+  if (FieldTraits<V>::is_sdf) {
+    // The list of blocks the allocation pass finds missing (with duplicates: every warp reports the distinct ones of its
+    // rays per round).  A ray enters at most numSteps * sqrt(3) / 8 + 4 blocks, so this capacity cannot overflow.
+    const size_t need = (size_t)m->W * m->H * ((size_t)(ap.numSteps > 0 ? ap.numSteps : 0) * 2 / 8 + 4);
+    if ((size_t)m->miss_capacity < need) {
+      if (need > ((size_t)1 << 30)) return fail(SE_B200_ERR_ARG, "mu / voxel size too large for the allocation request list");
+      CUDA_TRY(cudaStreamSynchronize(m->stream));
+      cudaFree(m->d_miss); m->d_miss = nullptr; m->miss_capacity = 0;
+      CUDA_TRY(cudaMalloc(&m->d_miss, need * sizeof(int)));
+      m->miss_capacity = (int)need;
+    }
+    miss.cells = m->d_miss; miss.capacity = m->miss_capacity;
+  }
 
   // counters: remember the pool sizes before the frame, clear the per-frame ones
   stage_begin(m, SE_B200_STAGE_ALLOC);
@@ -291,13 +348,20 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   const int parity = m->parity;
   const int threads = 256;
   const int grid_px = pixel_tile_blocks(m->W, m->H, threads);
+  // a1 rides along: a pending millimetre image is converted by the allocation kernel's threads (one pixel each)
+  DepthSource src;
+  src.mm = m->pending_mm; src.inW = m->pending_inW; src.ratio = m->pending_ratio;
   if (FieldTraits<V>::is_sdf) {
-    launch_pdl(k_alloc_sdf<V>, grid_px, threads, 0, m->stream, view, m->d_depth, ap);
+    launch_pdl(k_alloc_sdf<V>, grid_px, threads, 0, m->stream, view, m->d_depth, src, ap, miss, parity);
     if (int r = check_launch(m)) return r;
   } else {
-    launch_pdl(k_alloc_ofusion<V>, grid_px, threads, 0, m->stream, view, m->d_depth, ap, m->d_requests, m->max_requests);
+    launch_pdl(k_alloc_ofusion<V>, grid_px, threads, 0, m->stream, view, m->d_depth, src, ap, m->d_requests, m->max_requests);
     launch_pdl(k_alloc_first_key_chain<V>, 1, 1024, 0, m->stream, view, m->d_requests, m->max_requests);
     if (int r = check_launch(m, 2)) return r;
+  }
+  if (m->pending_mm) {
+    if (m->pending_slot >= 0) { CUDA_TRY(cudaEventRecord(m->aio.consumed[m->pending_slot], m->stream)); m->aio.consumed_valid[m->pending_slot] = true; }
+    m->pending_mm = nullptr; m->pending_slot = -1;
   }
   stage_end(m, SE_B200_STAGE_ALLOC);
 
@@ -327,23 +391,30 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
     }
     m->grid_integrate = m->num_sms * occ;
   }
-  launch_pdl(k_active_list<V>, m->num_sms * 2, threads, 0, m->stream, view, fp, m->d_active_list, parity);
+  // A/B: the list (and the deferred block creation) in a kernel of its own instead of inside the integrate kernel
+  static const bool list_kernel = [] { const char* e = std::getenv("SE_B200_LIST_KERNEL"); return e && e[0] == '1'; }();
+  int* status = m->d_status;
+  if (list_kernel) {
+    launch_pdl(k_prepare_blocks<V>, m->num_sms * 2, kListThreads, 0, m->stream, view, fp, m->d_active_list, miss, parity, status);
+    if (int r = check_launch(m)) return r;
+    status = nullptr;
+  }
   // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
   // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
   bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
   for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
   if (FieldTraits<V>::is_sdf) {
-    if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
-    else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, m->d_active_list, parity);
+    if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status);
+    else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status);
   } else {
     // check-free sequences + tabulated log-odds increment: the default (fuse 130 -> 59 us on box_room_ofusion1024,
     // same bits); SE_B200_OFUSION_FAST=0 or SE_B200_IEEE_DIV select the instantiation with the plain operators
     const char* e = std::getenv("SE_B200_OFUSION_FAST");
     const bool ofusion_fast = !(e && e[0] == '0');
-    if (fast && ofusion_fast && m->d_logodds) launch_pdl(k_integrate_ofusion<true>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity, (const float*)m->d_logodds);
-    else launch_pdl(k_integrate_ofusion<false>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, m->d_active_list, parity, (const float*)m->d_logodds);
+    if (fast && ofusion_fast && m->d_logodds) launch_pdl(k_integrate_ofusion<true>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status, (const float*)m->d_logodds);
+    else launch_pdl(k_integrate_ofusion<false>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status, (const float*)m->d_logodds);
   }
-  if (int r = check_launch(m, 2)) return r;
+  if (int r = check_launch(m, 1)) return r;
   stage_end(m, SE_B200_STAGE_FUSE);
   return SE_B200_OK;
 }
@@ -355,29 +426,40 @@ RaycastParams make_raycast_params(se_b200_map* m, const float* pose, const float
   rp.step = m->dim / (float)m->size;                                      // DenseSLAMSystem.cpp:197, :282
   rp.largestep = largestep;
   rp.W = m->W; rp.H = m->H; rp.use_tcmin = use_tcmin;
-#ifdef SE_RAY_UNIFORMS
-  // the same single-rounding IEEE operations RayWalk::init performs per thread (this file is compiled without FMA contraction)
+  // the ray-independent part of the ray set-up: the same single-rounding IEEE operations RayWalk::init performs per
+  // thread (this file is compiled without FMA contraction)
   rp.so = v3(rp.view.m[3] / m->dim + 1.f, rp.view.m[7] / m->dim + 1.f, rp.view.m[11] / m->dim + 1.f);
   rp.eps = 1.0f / (float)m->size;
   rp.near_n = rp.nearPlane / m->dim;
   rp.far_n = rp.farPlane / m->dim;
-#endif
+  // the check-free division / square-root sequences of the ray kernels (normalized3_fast, RayWalk::init_pre) are used
+  // when no operand can leave the normal float range; SE_B200_IEEE_DIV=1 forces the plain operators
+  bool fast = !getenv("SE_B200_IEEE_DIV");
+  for (int i = 0; i < 12 && fast; ++i) fast = normal_range(rp.view.m[i]);
+  rp.fast = fast ? 1 : 0;
   return rp;
+}
+
+template <class V, bool DENSE>
+void launch_raycast(se_b200_map* m, const RaycastParams& rp, unsigned long long* stats_dev, bool shade, V3 light) {
+  const int grid = pixel_tile_blocks(m->W, m->H, kRayThreads);
+  if (stats_dev) launch_pdl(k_raycast<V, DENSE, true, false>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev, light, (uchar4*)nullptr);
+  else if (shade) launch_pdl(k_raycast<V, DENSE, false, true>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, (unsigned long long*)nullptr, light, m->rt_dev);
+  else launch_pdl(k_raycast<V, DENSE, false, false>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, (unsigned long long*)nullptr, light, (uchar4*)nullptr);
 }
 
 template <class V>
 int raycast_impl(se_b200_map* m, const float* pose, const float* k, float mu, unsigned long long* stats_dev) {
+  if (int r = report_pool_error(m)) return r;
   const float step = m->dim / (float)m->size;
   const RaycastParams rp = make_raycast_params(m, pose, k, mu, kFarPlane, step * (float)kBlockSide, 1);
   stage_begin(m, SE_B200_STAGE_RAYCAST);
+  const bool shade = m->rt_dev && !stats_dev;
+  const V3 light = v3(pose[3], pose[7], pose[11]);             // the reuse path's light: view pose == raycast pose
   m->rt_valid = false;
-  if (m->rt_dev && !stats_dev) {
-    const V3 light = v3(pose[3], pose[7], pose[11]);           // the reuse path's light: view pose == raycast pose
-    launch_pdl(k_raycast_shade<V>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, light, m->rt_dev);
-    m->rt_light[0] = pose[3]; m->rt_light[1] = pose[7]; m->rt_light[2] = pose[11];
-    m->rt_valid = true;
-  } else if (stats_dev) launch_pdl(k_raycast<V, true>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev);
-  else launch_pdl(k_raycast<V, false>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, nullptr);
+  if (m->p.cmask) launch_raycast<V, true>(m, rp, stats_dev, shade, light);
+  else launch_raycast<V, false>(m, rp, stats_dev, shade, light);
+  if (shade) { m->rt_light[0] = pose[3]; m->rt_light[1] = pose[7]; m->rt_light[2] = pose[11]; m->rt_valid = true; }
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RAYCAST);
   return SE_B200_OK;
@@ -394,7 +476,8 @@ int render_volume_impl(se_b200_map* m, uchar4* out_dev, const float* view_pose, 
   const RaycastParams rp = make_raycast_params(m, view_pose, k, mu, kFarPlane * 2.0f, largestep, 0);   // DenseSLAMSystem.cpp:283-288
   const V3 light = v3(view_pose[3], view_pose[7], view_pose[11]);
   stage_begin(m, SE_B200_STAGE_RENDER);
-  if (reraycast) launch_pdl(k_render_volume<V>, ray_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
+  if (reraycast && m->p.cmask) launch_pdl(k_render_volume<V, true>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
+  else if (reraycast) launch_pdl(k_render_volume<V, false>, pixel_tile_blocks(m->W, m->H, kRayThreads), kRayThreads, 0, m->stream, m->view<V>(), rp, light, 1, m->d_vertex, m->d_normal, out_dev);
   else launch_pdl(k_render_shade, (m->W * m->H + 255) / 256, 256, 0, m->stream, m->d_vertex, m->d_normal, light, m->W * m->H, out_dev);
   if (int r = check_launch(m)) return r;
   stage_end(m, SE_B200_STAGE_RENDER);
@@ -468,6 +551,7 @@ int check_pool_error(se_b200_map* m) {
   if (err & kErrBlockPoolFull) return fail(SE_B200_ERR_POOL, "VoxelBlock pool exhausted: raise max_blocks");
   if (err & kErrNodePoolFull) return fail(SE_B200_ERR_POOL, "node pool exhausted: raise max_nodes");
   if (err & kErrKeyListFull) return fail(SE_B200_ERR_POOL, "octant request list exhausted");
+  if (err & kErrMissListFull) return fail(SE_B200_ERR_POOL, "allocation request list exhausted (requests of this frame were dropped)");
   return SE_B200_OK;
 }
 
@@ -578,12 +662,16 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
   m->stream = m->own_stream;
   for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { CREATE_TRY(cudaEventCreate(&m->ev_begin[i])); CREATE_TRY(cudaEventCreate(&m->ev_end[i])); }
   CREATE_TRY(cudaMallocHost(&m->h_counters, kNumCounters * sizeof(int)));
+  CREATE_TRY(cudaHostAlloc(&m->h_status, 4 * sizeof(int), cudaHostAllocMapped));
+  std::memset(m->h_status, 0, 4 * sizeof(int));
+  CREATE_TRY(cudaHostGetDevicePointer((void**)&m->d_status, m->h_status, 0));
   const size_t npx = (size_t)W * H;
   CREATE_TRY(cudaMalloc(&m->d_depth, npx * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_vertex, npx * 3 * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_normal, npx * 3 * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_rgba, npx * sizeof(uchar4)));
   CREATE_TRY(cudaMalloc(&m->d_active_list, (size_t)m->max_blocks * sizeof(int)));
+  CREATE_TRY(cudaMemsetAsync(m->d_active_list, 0xFF, (size_t)m->max_blocks * sizeof(int), m->stream));      // kEmpty: the list is streamed (ActiveList)
   CREATE_TRY(cudaMemsetAsync(m->d_depth, 0, npx * sizeof(float), m->stream));
   CREATE_TRY(cudaMemsetAsync(m->d_vertex, 0, npx * 3 * sizeof(float), m->stream));
   CREATE_TRY(cudaMemsetAsync(m->d_normal, 0, npx * 3 * sizeof(float), m->stream));
@@ -611,14 +699,15 @@ int se_b200_destroy(se_b200_map* m) {
   DeviceGuard guard(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->p.node_child); cudaFree(m->p.node_code); cudaFree(m->p.node_side); cudaFree(m->p.node_mask); cudaFree(m->p.node_value);
-  cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir); cudaFree(m->p.ndir);
+  cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir); cudaFree(m->p.ndir); cudaFree(m->p.cmask);
   cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
-  cudaFree(m->d_active_list); cudaFree(m->d_requests); cudaFree(m->d_logodds); cudaFree(m->d_track);
+  cudaFree(m->d_active_list); cudaFree(m->d_miss); cudaFree(m->d_requests); cudaFree(m->d_logodds); cudaFree(m->d_track);
   for (int i = 0; i < 8; ++i) { cudaFree(m->d_scaled_depth[i]); cudaFree(m->d_in_vertex[i]); cudaFree(m->d_in_normal[i]); }
   cudaFree(m->d_trackdata); cudaFree(m->d_partial); cudaFree(m->d_reduction); cudaFree(m->d_icp);
   cudaFree(m->d_mc_table); cudaFree(m->d_mesh);
   if (m->h_reduction) cudaFreeHost(m->h_reduction);
   if (m->h_counters) cudaFreeHost(m->h_counters);
+  if (m->h_status) cudaFreeHost(m->h_status);
   for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { if (m->ev_begin[i]) cudaEventDestroy(m->ev_begin[i]); if (m->ev_end[i]) cudaEventDestroy(m->ev_end[i]); }
   if (m->aio.ready) {
     cudaStreamSynchronize(m->aio.up); cudaStreamSynchronize(m->aio.down);
@@ -651,17 +740,35 @@ int se_b200_sync(se_b200_map* m) {
   return SE_B200_OK;
 }
 
-static int preprocess_common(se_b200_map* m, const uint16_t* src_dev, int inW, int inH) {
-  const int ratio = inW / m->W;
-  dim3 block(32, 8), grid((m->W + 31) / 32, (m->H + 7) / 8);
-  launch_pdl(k_mm2meters, grid, block, 0, m->stream, m->d_depth, src_dev, m->W, m->H, inW, ratio);
-  return check_launch(m);
+// a1 is deferred: remember where the millimetre image is; the allocation kernel of the next integrate converts it
+// (resolve_depth() does for any other consumer of the float image)
+static int preprocess_common(se_b200_map* m, const uint16_t* src_dev, int inW, int inH, int slot) {
+  (void)inH;
+  m->pending_mm = src_dev; m->pending_inW = inW; m->pending_ratio = inW / m->W; m->pending_slot = slot;
+  return SE_B200_OK;
 }
 static int check_ratio(se_b200_map* m, int inW, int inH) {
   // preprocessing.cpp:165-176 ("Invalid ratio." + exit(1) in the reference)
   if (inW < m->W || inH < m->H) return fail(SE_B200_ERR_ARG, "Invalid ratio.");
   if (inW % m->W != 0 || inH % m->H != 0) return fail(SE_B200_ERR_ARG, "Invalid ratio.");
   if (inW / m->W != inH / m->H) return fail(SE_B200_ERR_ARG, "Invalid ratio.");
+  return SE_B200_OK;
+}
+
+int se_b200_register_host_buffer(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail(SE_B200_ERR_ARG, "null buffer");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SE_B200_ERR_CUDA, "no CUDA device: this library has no CPU fallback"); }
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterMapped);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SE_B200_OK; }
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(SE_B200_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+  return SE_B200_OK;
+}
+
+int se_b200_unregister_host_buffer(void* ptr) {
+  if (!ptr) return fail(SE_B200_ERR_ARG, "null buffer");
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(SE_B200_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
   return SE_B200_OK;
 }
 
@@ -679,7 +786,7 @@ int se_b200_preprocess_depth_host(se_b200_map* m, const uint16_t* depth_mm, int 
   }
   stage_begin(m, SE_B200_STAGE_PREPROCESS);
   CUDA_TRY(cudaMemcpyAsync(m->d_depth_mm, depth_mm, bytes, cudaMemcpyHostToDevice, m->stream));
-  if (int r = preprocess_common(m, m->d_depth_mm, inW, inH)) return r;
+  if (int r = preprocess_common(m, m->d_depth_mm, inW, inH, -1)) return r;
   stage_end(m, SE_B200_STAGE_PREPROCESS);
   return SE_B200_OK;
 }
@@ -690,7 +797,7 @@ int se_b200_preprocess_depth_device(se_b200_map* m, const uint16_t* depth_mm_dev
   if (int r = check_ratio(m, inW, inH)) return r;
   DeviceGuard guard(m->device);
   stage_begin(m, SE_B200_STAGE_PREPROCESS);
-  if (int r = preprocess_common(m, depth_mm_dev, inW, inH)) return r;
+  if (int r = preprocess_common(m, depth_mm_dev, inW, inH, -1)) return r;
   stage_end(m, SE_B200_STAGE_PREPROCESS);
   return SE_B200_OK;
 }
@@ -730,10 +837,8 @@ int se_b200_preprocess_depth_host_async(se_b200_map* m, const uint16_t* depth_mm
   CUDA_TRY(cudaEventRecord(a.uploaded[s], a.up));
   CUDA_TRY(cudaStreamWaitEvent(m->stream, a.uploaded[s], 0));
   stage_begin(m, SE_B200_STAGE_PREPROCESS);
-  if (int r = preprocess_common(m, a.d_mm[s], inW, inH)) return r;
+  if (int r = preprocess_common(m, a.d_mm[s], inW, inH, s)) return r;      // `consumed[s]` is recorded by whoever converts the image
   stage_end(m, SE_B200_STAGE_PREPROCESS);
-  CUDA_TRY(cudaEventRecord(a.consumed[s], m->stream));
-  a.consumed_valid[s] = true;
   return SE_B200_OK;
 }
 
@@ -759,6 +864,7 @@ int se_b200_set_depth_m_host(se_b200_map* m, const float* depth_m) {
   REQUIRE_MAP(m);
   if (!depth_m) return fail(SE_B200_ERR_ARG, "depth_m is null");
   DeviceGuard guard(m->device);
+  m->pending_mm = nullptr; m->pending_slot = -1;           // this image replaces whatever preprocess left pending
   CUDA_TRY(cudaMemcpyAsync(m->d_depth, depth_m, (size_t)m->W * m->H * sizeof(float), cudaMemcpyHostToDevice, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return SE_B200_OK;
@@ -863,6 +969,7 @@ int se_b200_render_depth_host(se_b200_map* m, uint8_t* out) {
   if (!out) return fail(SE_B200_ERR_ARG, "out is null");
   DeviceGuard guard(m->device);
   const int n = m->W * m->H;
+  if (int r = resolve_depth(m)) return r;
   k_render_depth<<<(n + 255) / 256, 256, 0, m->stream>>>(m->d_rgba, m->d_depth, n, kNearPlane, kFarPlane);
   if (int r = check_launch(m)) return r;
   CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -1081,8 +1188,14 @@ int se_b200_query_rays(se_b200_map* m, const float* origin_dir, int n, float nea
   CUDA_TRY(dk.alloc((size_t)n * sizeof(unsigned long long)));
   CUDA_TRY(dt.alloc((size_t)n * 3 * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(dx.p, origin_dir, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-  if (m->field == SE_B200_SDF) k_query_ray<SdfVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
-  else k_query_ray<OfuVoxel><<<(n + kRayThreads - 1) / kRayThreads, kRayThreads, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+  const int qgrid = (n + kRayThreads - 1) / kRayThreads;
+  if (m->field == SE_B200_SDF) {
+    if (m->p.cmask) k_query_ray<SdfVoxel, true><<<qgrid, kRayThreads, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+    else k_query_ray<SdfVoxel, false><<<qgrid, kRayThreads, 0, m->stream>>>(m->view<SdfVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+  } else {
+    if (m->p.cmask) k_query_ray<OfuVoxel, true><<<qgrid, kRayThreads, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+    else k_query_ray<OfuVoxel, false><<<qgrid, kRayThreads, 0, m->stream>>>(m->view<OfuVoxel>(), (float*)dx.p, n, near_plane, far_plane, (unsigned long long*)dk.p, (float*)dt.p);
+  }
   if (int r = check_launch(m)) return r;
   if (first_block_key) CUDA_TRY(cudaMemcpyAsync(first_block_key, dk.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
   if (tinfo) CUDA_TRY(cudaMemcpyAsync(tinfo, dt.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
@@ -1112,7 +1225,7 @@ int se_b200_counters(se_b200_map* m, int32_t out[8]) {
   DeviceGuard guard(m->device);
   if (int r = fetch_counters(m)) return r;
   for (int i = 0; i < 8; ++i) out[i] = m->h_counters[i];
-  out[2] = m->h_counters[kCntActive0 + m->parity];
+  out[2] = m->h_counters[counter_slot(kCntActive, m->parity)];
   out[6] = m->h_counters[kCntKeysReport];
   out[7] = 0;
   return check_pool_error(m);
@@ -1128,7 +1241,7 @@ int se_b200_device_image(se_b200_map* m, int which, void** ptr) {
   REQUIRE_MAP(m);
   if (!ptr) return fail(SE_B200_ERR_ARG, "ptr is null");
   switch (which) {
-    case 0: *ptr = m->d_depth; break;
+    case 0: { DeviceGuard guard(m->device); if (int r = resolve_depth(m)) return r; } *ptr = m->d_depth; break;
     case 1: *ptr = m->d_vertex; break;
     case 2: *ptr = m->d_normal; break;
     default: return fail(SE_B200_ERR_ARG, "which must be 0..2");
@@ -1181,6 +1294,7 @@ int se_b200_filter_depth(se_b200_map* m, int filter, int levels) {
   REQUIRE_MAP(m);
   DeviceGuard guard(m->device);
   if (int r = ensure_tracking_buffers(m, levels)) return r;
+  if (int r = resolve_depth(m)) return r;
   if (filter) {
     Gauss5 gs;
     for (int i = 0; i < 5; ++i) { const int x = i - 2; gs.g[i] = expf(-(float)(x * x) / (2 * kGaussDelta * kGaussDelta)); }   // DenseSLAMSystem.cpp:111-118
@@ -1201,7 +1315,7 @@ int se_b200_track(se_b200_map* m, float pose_io[16], const float raycast_pose[16
   const dim3 tb(32, 8);
   // pyramid + per-level vertex / normal maps (DenseSLAMSystem.cpp:149-164)
   for (int i = 1; i < levels; ++i)
-    launch_pdl(k_half_sample, grid2d(m->W >> i, m->H >> i), tb, 0, m->stream, m->d_scaled_depth[i], m->d_scaled_depth[i - 1], m->W >> i, m->H >> i, kEDelta * 3, 1);
+    launch_pdl(k_half_sample, grid2d(m->W >> i, m->H >> i), tb, 0, m->stream, m->d_scaled_depth[i], m->d_scaled_depth[i - 1], m->W >> i, m->H >> i, m->W >> (i - 1), kEDelta * 3, 1);
   for (int i = 0; i < levels; ++i) {
     const float s = (float)(1 << i);
     const float ks[4] = { k[0] / s, k[1] / s, k[2] / s, k[3] / s };

@@ -27,12 +27,16 @@ namespace se_b200 {
 constexpr int kEmpty = -1;
 constexpr int kBusy = -2;
 
-// kCntActive0/1: the active-list length, double-buffered by frame parity (the list kernel of frame f counts into
-// slot f&1 and clears slot (f+1)&1 for the next frame -- no separate reset launch).
+// Line 0 (ints 0..31): pool bump allocators and per-frame bookkeeping.  The counters the integrate kernels' in-kernel
+// active list hammers (build_active_list) each sit in a 128-byte line of their own, double-buffered by frame parity
+// q = frame & 1 at  base + 32 q  -- frame f uses slot q and clears slot q ^ 1 for the next frame, so no reset launch is needed:
+//   kCntTicket  chunk tickets drawn          kCntDone  chunks finished          kCntActive  active-list length
+//   kCntMiss    length of the allocation pass's list of missing blocks (k_alloc_sdf appends, the integrate kernel creates)
 enum Counter { kCntNodes = 0, kCntBlocks = 1, kCntError = 3, kCntNewBlocksBase = 4, kCntNewNodesBase = 5,
-               kCntKeys = 6, kCntKeysReport = 7, kCntActive0 = 8, kCntActive1 = 9, kCntLastBlocks = 10, kCntLastNodes = 11,
-               kNumCounters = 16 };
-enum ErrorBits { kErrBlockPoolFull = 1, kErrNodePoolFull = 2, kErrKeyListFull = 4 };
+               kCntKeys = 6, kCntKeysReport = 7, kCntLastBlocks = 10, kCntLastNodes = 11, kCntBlocksBefore = 12, kCntNodesBefore = 13,
+               kCntTicket = 32, kCntDone = 96, kCntActive = 160, kCntMiss = 224, kNumCounters = 288 };
+SE_HD int counter_slot(int base, int parity) { return base + 32 * parity; }
+enum ErrorBits { kErrBlockPoolFull = 1, kErrNodePoolFull = 2, kErrKeyListFull = 4, kErrMissListFull = 8 };
 
 // ---- field types (se_denseslam/include/se/volume_traits.hpp:41-72) --------------------
 struct SdfVoxel { float x; float y; };                                    // tsdf, weight
@@ -77,7 +81,16 @@ template <class V> struct MapView {
   // at offset (8^l - 8) / 7).  It costs 1/7 of the block directory and lets the multi-level (OFusion)
   // allocation pass test "does the octant at level l exist" with one load.  nullptr => tree descent.
   int* ndir;
+  // Children masks by implicit position: the octant with heap index g (root 0, child s of g = 8 g + 1 + s, s = x | y<<1 | z<<2)
+  // has one byte, bit s set <=> its child s exists -- Node::children_mask_ addressed by where the octant IS instead of
+  // by a pool index, for the levels 0 .. leaves_level-1: (8^leaves_level - 1) / 7 bytes (37 KB at 512^3, 2.4 MB at 2048^3).
+  // The ray walk (RayWalk, se_kernels.cuh) reads one byte per descent instead of one child pointer per step, and the
+  // byte's address follows from the ray's position, not from the previous load.  nullptr => the walk chases node_child.
+  unsigned char* cmask;
 };
+
+// heap index of the first octant of `level` (= number of octants above it)
+SE_HD unsigned heap_level_offset(int level) { return (unsigned)(((1ull << (3 * level)) - 1ull) / 7ull); }
 
 // index of the level-`level` octant containing voxel (x, y, z) in MapView::ndir
 template <class V>
@@ -188,19 +201,19 @@ __device__ __forceinline__ float get_fine_x(const MapView<V>& m, BlockCache& c, 
 
 // gather_points (interp_gather.hpp:105-237): the 8 corners are grouped by the block they fall
 // in; one fetch per group; a missing block reads empty() in cases 0..6 and initValue() in the
-// all-axes-crossing case 7.  The corners span at most two blocks per axis.  One straight-line path for
-// all 8 crossing cases (a warp almost always holds both crossing and non-crossing lanes, so a separate
-// fast path would only add its instructions to the slow one): corner s = (ox, oy, oz) lies in block
-// id[s & crossmask]; the eight ids are built with selects, fetching only the blocks whose stepped axes all
-// cross (usually none), and stay in registers.
+// all-axes-crossing case 7 -- the same number for both field types (volume_traits.hpp:41-72), and what the pool's
+// never-allocated payload holds.  The corners span at most two blocks per axis: corner s = (ox, oy, oz) lies in the
+// block at directory cell  cell0 + (ox & cx) + G (oy & cy) + G^2 (oz & cz),  c* = "the base voxel is the last of its block
+// along *".
+//
+// gather_points_general: any position, with or without the directory (volume faces, SE_B200_DISABLE_DIRECTORY).
 template <class V>
-__device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int bx, int by, int bz, float p[8]) {
+__device__ __forceinline__ void gather_points_general(const MapView<V>& m, int bx, int by, int bz, float p[8]) {
   const bool cx = (bx & 7) == 7, cy = (by & 7) == 7, cz = (bz & 7) == 7;
   const int Bx = bx >> 3, By = by >> 3, Bz = bz >> 3;
-  auto present = [&](int b) -> int { return b < 0 ? m.max_blocks : b; };      // unallocated -> the initValue() payload
-  auto fetch = [&](int ox, int oy, int oz) -> int { return present(fetch_block_cell(m, Bx + ox, By + oy, Bz + oz)); };
+  auto fetch = [&](int ox, int oy, int oz) -> int { const int b = fetch_block_cell(m, Bx + ox, By + oy, Bz + oz); return b < 0 ? m.max_blocks : b; };
   int id[8];
-  id[0] = present(fetch_block_cached(m, c, bx, by, bz));
+  id[0] = fetch(0, 0, 0);
   id[1] = cx ? fetch(1, 0, 0) : id[0];
   id[2] = cy ? fetch(0, 1, 0) : id[0];
   id[3] = cx ? (cy ? fetch(1, 1, 0) : id[1]) : id[2];
@@ -208,8 +221,6 @@ __device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c
   id[5] = cx ? (cz ? fetch(1, 0, 1) : id[1]) : id[4];
   id[6] = cy ? (cz ? fetch(0, 1, 1) : id[2]) : id[4];
   id[7] = cx ? (cy ? (cz ? fetch(1, 1, 1) : id[3]) : id[5]) : id[6];
-  // a missing block reads empty().x in the cases 0..6 and initValue().x in case 7 -- the same number for both
-  // field types (volume_traits.hpp:41-72), and what the pool's never-allocated payload holds
   const int xo[2] = { bx & 7, (bx + 1) & 7 };
   const int yo[2] = { (by & 7) << 3, ((by + 1) & 7) << 3 };
   const int zo[2] = { (bz & 7) << 6, ((bz + 1) & 7) << 6 };
@@ -220,12 +231,63 @@ __device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c
   }
 }
 
+// The usual case -- the base voxel and its +1 neighbours inside the volume, directory present -- straight-line: the seven
+// neighbour-block ids are PREDICATED loads from the directory (a lane whose corner stays in the base block issues no
+// memory operation and keeps the base id).  A warp almost always holds lanes of every crossing case, so branches on the
+// case would make every warp run every branch; predication costs one issue slot per possible neighbour instead.
+template <class V>
+__device__ __forceinline__ bool gather_is_interior(const MapView<V>& m, int bx, int by, int bz) {
+  const unsigned lim = (unsigned)(m.size - 1);
+  return m.dir && (((unsigned)bx < lim) & ((unsigned)by < lim) & ((unsigned)bz < lim));
+}
+template <class V>
+__device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c, int bx, int by, int bz, float p[8]) {
+  const int G = m.dir_dim;
+  const bool cx = (bx & 7) == 7, cy = (by & 7) == 7, cz = (bz & 7) == 7;
+  const int b0 = fetch_block_cached(m, c, bx, by, bz);
+  const int id0 = b0 < 0 ? m.max_blocks : b0;                 // unallocated -> the initValue() payload
+  const int* cell0 = m.dir + (((bz >> 3) * G + (by >> 3)) * G + (bx >> 3));
+  const int ox = cx ? 1 : 0, oy = cy ? G : 0, oz = cz ? G * G : 0;
+  int id[8];
+  id[0] = id0;
+  id[1] = ldg_if(cx, cell0 + ox, b0);
+  id[2] = ldg_if(cy, cell0 + oy, b0);
+  id[3] = ldg_if(cx | cy, cell0 + (ox + oy), b0);
+  id[4] = ldg_if(cz, cell0 + oz, b0);
+  id[5] = ldg_if(cx | cz, cell0 + (ox + oz), b0);
+  id[6] = ldg_if(cy | cz, cell0 + (oy + oz), b0);
+  id[7] = ldg_if(cx | cy | cz, cell0 + (ox + oy + oz), b0);
+  const int xo[2] = { bx & 7, (bx + 1) & 7 };
+  const int yo[2] = { (by & 7) << 3, ((by + 1) & 7) << 3 };
+  const int zo[2] = { (bz & 7) << 6, ((bz + 1) & 7) << 6 };
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int off = xo[i & 1] + yo[(i >> 1) & 1] + zo[(i >> 2) & 1];
+    const int b = i == 0 ? id0 : (id[i] < 0 ? m.max_blocks : id[i]);
+    p[i] = load_x(m.block_data + (size_t)b * kBlockVoxels + off);
+  }
+}
+
 // Octree::interp (octree.hpp:541-563), pos in voxel units
+__device__ __forceinline__ float trilinear(const float (&p)[8], float fx, float fy, float fz) {
+  return (((p[0] * (1 - fx) + p[1] * fx) * (1 - fy)
+         + (p[2] * (1 - fx) + p[3] * fx) * fy) * (1 - fz)
+        + ((p[4] * (1 - fx) + p[5] * fx) * (1 - fy)
+         + (p[6] * (1 - fx) + p[7] * fx) * fy) * fz);
+}
+// positions on the volume's faces / maps without the directory: out of line (rays almost never sample there)
+template <class V>
+__device__ __noinline__ float interp_field_general(const MapView<V>& m, int bx, int by, int bz, float fx, float fy, float fz) {
+  float p[8];
+  gather_points_general(m, bx, by, bz, p);
+  return trilinear(p, fx, fy, fz);
+}
 template <class V>
 __device__ __forceinline__ float interp_field(const MapView<V>& m, BlockCache& c, V3 pos) {
   const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
   const float fx = pos.x - flx, fy = pos.y - fly, fz = pos.z - flz;
   const int bx = max((int)flx, 0), by = max((int)fly, 0), bz = max((int)flz, 0);
+  if (!gather_is_interior(m, bx, by, bz)) return interp_field_general(m, bx, by, bz, fx, fy, fz);
   float p[8];
   gather_points(m, c, bx, by, bz, p);
   return (((p[0] * (1 - fx) + p[1] * fx) * (1 - fy)
@@ -321,13 +383,8 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*th
   const int hi = m.size - 1;
   // every clamped coordinate inside [0, hi]  <=>  -1 <= b <= hi on each axis
   const bool inside = ((unsigned)(b0 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b1 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b2 + 1) <= (unsigned)(hi + 1));
-#ifdef SE_GRAD_NBHD
-  typedef unsigned VoxelIndex;      // experiment: block * 512 + offset as unsigned -> pools up to 2^23 - 1 blocks stay on this path
+  typedef unsigned VoxelIndex;      // block * 512 + offset, unsigned: pools up to 2^23 - 1 blocks (32 GB of SDF payload) stay on this path
   const int kIndexablePool = (1 << 23) - 1;
-#else
-  typedef int VoxelIndex;
-  const int kIndexablePool = (1 << 22) - 1;
-#endif
   if (!inside || m.max_blocks > kIndexablePool) return grad_field_general(m, b0, b1, b2, pos.x - flx, pos.y - fly, pos.z - flz, scale);
   float g[kGradSamples];
   const int x4[4] = { max(b0 - 1, 0), max(b0, 0), min(b0 + 1, hi), min(b0 + 2, hi) };
@@ -342,11 +399,10 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*th
     rz[j] = ((z4[j] >> 3) - Bz) << 1; oz[j] = (z4[j] & 7) << 6;
   }
   const int t = threadIdx.x;
-#ifdef SE_GRAD_NBHD
-  // EXPERIMENT (opt-in, not in the default build): the 2x2x2 directory cells from one base index.
-  // (Bx, By, Bz) is inside the grid here, only the +1 cells can fall outside it: such a cell re-reads an inside one
-  // and the value is discarded.  Eight generic lookups cost ~31 instructions each (three bounds tests, the index
-  // arithmetic, the directory test); this is ~8 per cell.
+  // The 2x2x2 directory cells from one base index.  (Bx, By, Bz) is inside the grid here, only the +1 cells can fall
+  // outside it: such a cell re-reads an inside one and the value is discarded.  (Eight generic lookups cost ~31
+  // instructions each -- three bounds tests, the index arithmetic, the directory test; this is ~8 per cell.
+  // Measured on the device, round 2: raycast 42.0 -> 41.4 us at 512^3, 130 -> 90 us at 2048^3 with its 4 M-block pool.)
   if (m.dir) {
     const int G = m.dir_dim;
     const bool ux = Bx + 1 < G, uy = By + 1 < G, uz = Bz + 1 < G;
@@ -359,12 +415,12 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*th
       const int lo = __ldg(m.dir + cell), up = __ldg(m.dir + cell + dxo);
       pairs[r][t] = make_int2((row_ok && lo >= 0) ? lo : m.max_blocks, (row_ok && ux && up >= 0) ? up : m.max_blocks);
     }
-  } else
-#endif
+  } else {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int lo = fetch_block_cell(m, Bx, By + (r & 1), Bz + (r >> 1)), up = fetch_block_cell(m, Bx + 1, By + (r & 1), Bz + (r >> 1));
-    pairs[r][t] = make_int2(lo < 0 ? m.max_blocks : lo, up < 0 ? m.max_blocks : up);
+    for (int r = 0; r < 4; ++r) {
+      const int lo = fetch_block_cell(m, Bx, By + (r & 1), Bz + (r >> 1)), up = fetch_block_cell(m, Bx + 1, By + (r & 1), Bz + (r >> 1));
+      pairs[r][t] = make_int2(lo < 0 ? m.max_blocks : lo, up < 0 ? m.max_blocks : up);
+    }
   }
   struct Row { VoxelIndex lo, up; };
   auto row = [&](int jy, int jz) {
@@ -435,6 +491,7 @@ template <class V>
 __device__ __forceinline__ int find_or_create(const MapView<V>& m, unsigned long long code, int target_level, bool& created_target) {
   created_target = false;
   int n = 0;
+  unsigned g = 0;                       // heap index of node n (MapView::cmask)
   int edge = m.size >> 1;
   for (int level = 1; level <= target_level; ++level, edge >>= 1) {
     const int slot = key_child_id(code, level, m.max_level);
@@ -475,6 +532,7 @@ __device__ __forceinline__ int find_or_create(const MapView<V>& m, unsigned long
           }
           if (level == target_level) created_target = true;
           atomicOr(m.node_mask + n, 1u << slot);
+          if (m.cmask) atomicOr(reinterpret_cast<unsigned*>(m.cmask) + (g >> 2), (1u << slot) << ((g & 3u) * 8u));
           __threadfence();
           atomicExch(p, idx);
           if (level == m.leaves_level && m.dir) {
@@ -495,6 +553,7 @@ __device__ __forceinline__ int find_or_create(const MapView<V>& m, unsigned long
       }
     }
     n = c;
+    g = 8u * g + 1u + (unsigned)slot;
   }
   return n;
 }

@@ -19,6 +19,19 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// ---- inter-warp hand-off through global memory (the integrate kernels' in-kernel active list) --------
+// acquire load of a counter another warp releases with __threadfence() + atomicAdd; the poll backs off with nanosleep
+__device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void poll_backoff() { asm volatile("nanosleep.u32 64;" ::: "memory"); }
+
+// ---- predicated read-only load: `pred ? __ldg(p) : otherwise` as one predicated LDG, never a branch ----
+__device__ __forceinline__ int ldg_if(bool pred, const int* p, int otherwise) {
+  int v;
+  asm("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n mov.s32 %0, %3;\n @q ld.global.nc.s32 %0, [%1];\n}" : "=r"(v) : "l"(p), "r"((int)pred), "r"(otherwise));
+  return v;
+}
+
 // ---- MUFU approximations (the seeds of rcp_rn / sqrt_rn in se_kernels.cuh) ------------------------
 __device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }

@@ -52,11 +52,13 @@ __global__ void __launch_bounds__(256) k_bilateral(float* __restrict__ out, cons
   out[pos] = t / sum;
 }
 
-__global__ void __launch_bounds__(256) k_half_sample(float* __restrict__ out, const float* __restrict__ in, int outW, int outH, float e_d, int r) {
+// inW: the parent level's real row stride (in.width(), preprocessing.cpp:209,217) -- 2 outW + 1 when the parent's width is
+// odd; the clamp stays at 2 out - 1 as in the reference (:214-216)
+__global__ void __launch_bounds__(256) k_half_sample(float* __restrict__ out, const float* __restrict__ in, int outW, int outH, int inW, float e_d, int r) {
   pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= outW || y >= outH) return;
-  const int inW = outW * 2, cx = 2 * x, cy = 2 * y;
+  const int cx = 2 * x, cy = 2 * y;
   float sum = 0.f, t = 0.f;
   const float center = in[cx + cy * inW];
   for (int i = -r + 1; i <= r; ++i)

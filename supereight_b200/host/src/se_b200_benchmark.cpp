@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
   config.camera = Eigen::Vector4f(481.2f, 480.f, 320.f, 240.f);
   config.pyramid = {10, 5, 4};
   config.integration_rate = 2; config.rendering_rate = 4; config.mu = 0.1f; config.compute_size_ratio = 1;
-  std::string poses_file, dump_file, map_file, mesh_file;
+  std::string poses_file, dump_file, map_file, mesh_file, load_file;
   int max_frames = -1;
   bool use_tracking = false;      // -t 1: track with ICP after the first 4 frames instead of reading the pose file
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -79,6 +79,7 @@ int main(int argc, char** argv) {
     else if (a == "-d") dump_file = v;
     else if (a == "-M") mesh_file = v;
     else if (a == "-b") map_file = v;
+    else if (a == "-L") load_file = v;                      // a map file (e.g. one written by the reference's Octree::save) to load, raycast and dump
     else if (a == "-n") max_frames = std::atoi(v);
     else if (a == "-t") use_tracking = std::atoi(v) != 0;
     else if (a == "-f") config.bilateralFilter = std::atoi(v) != 0;
@@ -166,6 +167,23 @@ int main(int argc, char** argv) {
     std::ofstream os(dump_file, std::ios::binary);
     put(os, map->block_keys); put(os, map->block_voxels); put(os, map->node_codes); put(os, map->node_values);
     put(os, vertex); put(os, normal); put(os, volumeRender); put(os, depthRender); put(os, trackRender);
+    if (!load_file.empty()) {
+      // N3, the other direction: a map file from elsewhere -> se::MapSnapshot::load -> setMap() on a fresh pipeline -> raycast from
+      // the stream's last pose; its content as re-exported by the device and the vertex / normal maps go to the dump
+      se::MapSnapshot in;
+      if (!in.load(load_file)) { std::cerr << "cannot read " << load_file << std::endl; return 1; }
+      DenseSLAMSystem third(Eigen::Vector2i(cw, ch), config.volume_resolution, config.volume_size, init_pose, config.pyramid, config);
+      third.setMap(in);
+      Eigen::Matrix4f last = pipeline.getPose();
+      last(0, 3) -= init_pose.x(); last(1, 3) -= init_pose.y(); last(2, 3) -= init_pose.z();
+      third.setPose(last);
+      third.raycasting(camera, config.mu, 3);
+      std::shared_ptr<se::MapSnapshot> back;
+      third.getMap(back);
+      third.getVertexNormal(vertex, normal);
+      put(os, back->block_keys); put(os, back->block_voxels); put(os, back->node_codes); put(os, back->node_values);
+      put(os, vertex); put(os, normal);
+    }
   }
   return 0;
 }

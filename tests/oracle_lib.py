@@ -116,6 +116,12 @@ def load(kind: str = "parity"):
     _set(lib, "seo_reset_counters", "argtypes", [C.c_void_p])
     _set(lib, "seo_get_counters", "argtypes", [C.c_void_p, C.c_void_p])
     _set(lib, "seo_set_omp_threads", "argtypes", [C.c_int])
+    _set(lib, "seo_save_map", "argtypes", [C.c_void_p, C.c_char_p])
+    _set(lib, "seo_load_map", "restype", C.c_void_p)
+    _set(lib, "seo_load_map", "argtypes", [C.c_char_p, C.c_float])
+    _set(lib, "seo_map_size", "argtypes", [C.c_void_p])
+    _set(lib, "seo_map_dim", "restype", C.c_float)
+    _set(lib, "seo_map_dim", "argtypes", [C.c_void_p])
     _libs[kind] = lib
     return lib
 
@@ -147,6 +153,21 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    # ---- N3 (reference build only): Octree::save, and Octree::load into a stand-alone octree -----------------------
+    def save_map(self, path: str):
+        self.lib.seo_save_map(self.h, path.encode())
+
+    @classmethod
+    def load_map(cls, field: int, path: str, kind: str, dim_fix: float = 0.0):
+        """An Oracle whose handle wraps an octree read by the reference's own Octree::load (block / node / point queries
+        only).  dim_fix > 0 repairs dim_, which the reference reads as an int (octree.hpp:921-923)."""
+        o = cls.__new__(cls)
+        o.lib = load(kind)
+        o.field, o.vdtype = field, FIELD_DTYPE[field]
+        o.h = C.c_void_p(o.lib.seo_load_map(path.encode(), dim_fix))
+        o.size, o.dim, o.W, o.H = o.lib.seo_map_size(o.h), float(o.lib.seo_map_dim(o.h)), 0, 0
+        return o
 
     def preprocess(self, depth_mm: np.ndarray):
         d = np.ascontiguousarray(depth_mm, dtype=np.uint16)

@@ -17,6 +17,7 @@
 #pragma once
 #include <algorithm>
 #include <chrono>
+#include <cfenv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -319,6 +320,15 @@ inline int __float2int_rd(float f) {
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
+// add.rm.f32 (round toward minus infinity)
+inline float __fadd_rd(float a, float b) {
+  const int old = std::fegetround();
+  std::fesetround(FE_DOWNWARD);
+  volatile float va = a, vb = b;
+  volatile float r = va + vb;
+  std::fesetround(old);
+  return r;
+}
 
 // atomics: one OS thread, fibers switch only at collectives -> plain read-modify-write
 template <class T> inline T atomicAdd(T* p, T v) { const T o = *p; *p = o + v; return o; }
@@ -348,7 +358,7 @@ using std::isinf;
 
 // ---- runtime API -----------------------------------------------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorHostMemoryAlreadyRegistered = 712 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 typedef struct CUstream_st* cudaStream_t;
 struct CUevent_st { std::chrono::steady_clock::time_point t; };
@@ -378,6 +388,11 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) {
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+constexpr unsigned cudaHostAllocMapped = 2, cudaHostRegisterDefault = 0, cudaHostRegisterMapped = 2;
+template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { return cudaMallocHost(p, n); }
+inline cudaError_t cudaHostGetDevicePointer(void** dev, void* host, unsigned) { *dev = host; return cudaSuccess; }
+inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }

@@ -13,6 +13,12 @@ namespace se_b200 {
 
 __device__ __forceinline__ void pdl_prologue() {}
 
+__device__ __forceinline__ int ld_acquire(const int* p) { return *(const volatile int*)p; }
+__device__ __forceinline__ void st_release(int* p, int v) { *(volatile int*)p = v; }
+__device__ __forceinline__ void poll_backoff() { simt::yield(); }
+
+__device__ __forceinline__ int ldg_if(bool pred, const int* p, int otherwise) { return pred ? *p : otherwise; }
+
 __device__ __forceinline__ float mufu_rcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ float mufu_rsq(float x) { return (float)(1.0 / std::sqrt((double)x)); }
 

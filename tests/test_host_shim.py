@@ -34,10 +34,11 @@ def write_stream(tmp, frames, dim, W, H, k, scene="plane"):
     return raw, poses_path, depth, poses
 
 
-def read_dump(path, vdtype):
+def read_dump(path, vdtype, loaded=False):
     buf = open(path, "rb").read()
     off, out = 0, []
-    for dt in (np.uint64, vdtype, np.uint64, vdtype, np.float32, np.float32, np.uint8, np.uint8, np.uint8):
+    extra = (np.uint64, vdtype, np.uint64, vdtype, np.float32, np.float32) if loaded else ()
+    for dt in (np.uint64, vdtype, np.uint64, vdtype, np.float32, np.float32, np.uint8, np.uint8, np.uint8) + extra:
         n = struct.unpack_from("<Q", buf, off)[0]; off += 8
         a = np.frombuffer(buf, dtype=dt, count=n, offset=off); off += n * np.dtype(dt).itemsize
         out.append(a)
@@ -112,3 +113,64 @@ def test_shim_frame_loop_matches_oracle(tmp_path, field, mu):
         assert np.array_equal(gd["y"], data["y"])
     assert np.array_equal(dep.reshape(H, W, 4), o.render_depth())
     assert np.all(trk.reshape(H, W, 4)[..., :3] == np.array([255, 128, 128], np.uint8))     # result 0 -> default colour (rendering.cpp:203-208)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field,mu", [("sdf", 0.1), ("ofusion", 0.03)])
+def test_map_file_exchange_with_the_reference(tmp_path, field, mu):
+    """N3 against the reference's own Octree::save / Octree::load (oracle/_ref, octree.hpp:897-950), both directions:
+    (1) the map the CUDA kernels built, written by the shim (`-b`), is read by the reference's loader: same octree (as far
+        as that loader restores one: see tests/test_map_file.py) -- and the file holds the oracle's payloads byte for byte;
+    (2) a map the REFERENCE built and saved is loaded by the shim (`-L`: MapSnapshot::load + setMap) into the device pools:
+        re-exported identical, and its raycast is the reference's raycast of that map, bit for bit."""
+    if not oracle_lib.have_reference_build():
+        pytest.skip("oracle/_ref (the reference build) is absent")
+    import test_map_file as tmf
+    W, H, size, dim, frames = 160, 120, 256, 4.8, 4
+    k = (120.3, 120.0, 80.0, 60.0)
+    scene = "plane" if field == "sdf" else "room"
+    raw, poses_path, depth, poses = write_stream(str(tmp_path), frames, dim, W, H, k, scene=scene)
+    fid = oracle_lib.SDF if field == "sdf" else oracle_lib.OFUSION
+    ref = oracle_lib.Oracle(fid, size, dim, W, H, kind=f"ref_{field}")
+    ref.lib.seo_set_omp_threads(1)
+    for f in range(frames):
+        ref.preprocess(depth[f]); ref.integrate(poses[f], k, mu, f)
+    ref.raycast(poses[-1], k, mu)
+    refmap, shimmap, dump = (os.path.join(str(tmp_path), n) for n in ("reference.bin", "shim.bin", "dump.bin"))
+    ref.save_map(refmap)
+    r = subprocess.run([exe(field), "-i", raw, "-g", poses_path, "-v", str(size), "-s", str(dim), "-m", str(mu), "-r", "1", "-z", "1",
+                        "-k", ",".join(str(v) for v in k), "-o", os.path.join(str(tmp_path), "log.tsv"), "-d", dump, "-b", shimmap, "-L", refmap],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # (1) device map -> shim file -> the reference's reader, and the file's payloads against the reference's own map
+    back = oracle_lib.Oracle.load_map(fid, shimmap, f"ref_{field}", dim_fix=dim)
+    size_f, dim_f, nodes, blocks = tmf.parse_map_file(shimmap, ref.vdtype)
+    keys, coords, _, data = ref.blocks_sorted()
+    codes, side, _, values = ref.nodes_sorted()
+    assert (size_f, np.float32(dim_f)) == (size, np.float32(dim)) and len(keys) > 300
+    assert np.array_equal(blocks["code"], keys) and np.array_equal(blocks["coords"], coords)
+    assert np.array_equal(nodes["code"], codes) and np.array_equal(nodes["side"], side)
+    if field == "sdf":
+        assert blocks["voxels"].tobytes() == data.tobytes() and nodes["value"].tobytes() == values.tobytes()
+        tmf.same_octree(ref, back, reloaded_by_reference=True)
+    else:
+        np.testing.assert_allclose(blocks["voxels"]["x"], data["x"], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(blocks["voxels"]["y"], data["y"])
+        kb, cb, _, _ = back.blocks_sorted(with_data=False)
+        assert np.array_equal(kb, keys) and np.array_equal(cb, coords) and np.array_equal(back.nodes_sorted()[0], codes)
+    back.close()
+    # (2) reference map -> file -> shim -> device: content and raycast
+    out = read_dump(dump, ref.vdtype, loaded=True)
+    lk, ld, lc, lv, lvert, lnorm = out[9:]
+    assert np.array_equal(lk, keys) and np.array_equal(lc, codes)
+    assert ld.tobytes() == data.tobytes() and lv.tobytes() == values.tobytes()
+    lvert = lvert.reshape(H, W, 3); lnorm = lnorm.reshape(H, W, 3)
+    rv, rn = ref.vertex(), ref.normal()
+    assert (rn[..., 0] != -2.0).sum() > 0.2 * W * H
+    if field == "sdf":
+        assert np.array_equal(lvert.view(np.uint32), rv.view(np.uint32)) and np.array_equal(lnorm.view(np.uint32), rn.view(np.uint32))
+    else:
+        hit_g, hit_r = lnorm[..., 0] != -2.0, rn[..., 0] != -2.0
+        assert (hit_g != hit_r).mean() < 2e-3
+        both = hit_g & hit_r
+        np.testing.assert_allclose(lvert[both], rv[both], rtol=1e-4, atol=1e-5)

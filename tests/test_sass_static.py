@@ -74,16 +74,20 @@ def test_built_for_sm_100a():
 
 def test_register_budgets(resources):
     # raycast: 8 CTAs x 128 threads per SM need <= 64 registers; a few spilled words are accepted, a frame of kilobytes is not
-    for name in ("k_raycast<SdfVoxel, false>", "k_raycast<OfuVoxel, false>"):
+    # (template arguments: field, DENSE walk, COUNT, SHADE)
+    ray = [n for n in resources if n.startswith("k_raycast<")]
+    assert len(ray) >= 8, ray
+    for name in ray:
         assert resources[name]["REG"] <= 64 and resources[name]["STACK"] <= 256, (name, resources[name])
-    # integrate (SDF): 3 CTAs x 256 threads per SM -> <= 85 registers, no stack; its 64 KiB of stage buffers are dynamic smem
+    # integrate (SDF): 4 CTAs x 256 threads per SM -> <= 64 registers, no stack; its 32 KiB of half-block stage buffers are dynamic smem
     for name in ("k_integrate_sdf<true>", "k_integrate_sdf<false>"):
-        assert resources[name]["REG"] <= 80 and resources[name]["STACK"] == 0, (name, resources[name])
-    # integrate (OFusion): 4 CTAs x 256 threads -> <= 64
-    for name in ("k_integrate_ofusion<true>", "k_integrate_ofusion<false>"):
         assert resources[name]["REG"] <= 64 and resources[name]["STACK"] == 0, (name, resources[name])
-    # allocation: 4 CTAs x 256 threads -> <= 64, the per-thread block lists live in (static) shared memory
-    assert resources["k_alloc_sdf<SdfVoxel>"]["REG"] <= 64 and resources["k_alloc_sdf<SdfVoxel>"]["STACK"] == 0
+    # integrate (OFusion): 4 CTAs x 256 threads -> <= 64
+    # (the plain-operator fallback may spill a word or two: it carries the in-kernel list builder's frustum test as well)
+    for name, stack in (("k_integrate_ofusion<true>", 0), ("k_integrate_ofusion<false>", 16)):
+        assert resources[name]["REG"] <= 64 and resources[name]["STACK"] <= stack, (name, resources[name])
+    # allocation: 5 CTAs x 256 threads -> <= 51, the per-thread block lists live in (static) shared memory
+    assert resources["k_alloc_sdf<SdfVoxel>"]["REG"] <= 51 and resources["k_alloc_sdf<SdfVoxel>"]["STACK"] <= 64
     assert resources["k_alloc_ofusion<OfuVoxel>"]["REG"] <= 64 and resources["k_alloc_ofusion<OfuVoxel>"]["STACK"] == 0
 
 
@@ -99,7 +103,7 @@ def test_integrate_pipeline_is_tma_plus_mbarrier_and_packed_fp32(sass):
 
 
 def test_every_per_frame_kernel_uses_programmatic_dependent_launch(sass):
-    for k in ("k_mm2meters", "k_alloc_sdf", "k_alloc_ofusion", "k_alloc_first_key_chain", "k_active_list", "k_integrate_sdf",
+    for k in ("k_mm2meters", "k_alloc_sdf", "k_alloc_ofusion", "k_alloc_first_key_chain", "k_integrate_sdf",
               "k_integrate_ofusion", "k_raycast", "k_render_shade", "k_render_volume"):
         for name, ops in kernels(sass, k).items():
             assert has(ops, "ACQBULK") >= 1, (name, "griddepcontrol.wait missing")

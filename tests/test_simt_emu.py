@@ -81,31 +81,6 @@ def test_tree_descent_without_the_directories(emu_lib):
     run_pytest_on_emu(emu_lib, "tests/test_gpu_parity.py::test_map_export_import_round_trip", {"SE_B200_DISABLE_DIRECTORY": "1"})
 
 
-EXPERIMENTS = [
-    # csrc/se_integrate_staged.cuh: half-block pipeline stages, 4 CTAs per SM
-    (("-DSE_INT_STAGE_SLICES=4",), "_stage4", ["tests/test_gpu_parity.py::test_sdf_512_full_frame_sequence_bit_exact",
-                                               "tests/test_gpu_parity.py::test_sdf_ieee_division_fallback_paths"]),
-    # raycast: the gradient's 2x2x2 directory cells from one base index (se_map.cuh grad_field) and the ray-independent
-    # quantities of the ray set-up computed once on the host (se_kernels.cuh RayWalk::init_pre)
-    (("-DSE_GRAD_NBHD", "-DSE_RAY_UNIFORMS"), "_ray", ["tests/test_gpu_parity.py::test_point_queries_match_oracle_all_gather_cases",
-                                                       "tests/test_gpu_parity.py::test_sdf_camera_outside_and_partially_out_of_volume",
-                                                       "tests/test_gpu_parity.py::test_sdf_negative_fy_camera"]),
-    # ray kernels with 32x1 pixel tiles per warp instead of 8x4 (se_kernels.cuh tile_pixel)
-    (("-DSE_RAY_TILE_32X1",), "_t32", ["tests/test_gpu_parity.py::test_ragged_image_sizes_and_tiny_volume",
-                                       "tests/test_gpu_parity.py::test_sdf_camera_outside_and_partially_out_of_volume"]),
-]
-
-
-@pytest.mark.parametrize("defines,suffix,nodeids", EXPERIMENTS, ids=[e[1][1:] for e in EXPERIMENTS])
-def test_opt_in_experiments_are_bit_exact(emu_lib, defines, suffix, nodeids):
-    """The compile-time experiments (not in the default build) stay bit-exact against the oracle, so
-    that each is ready for its A/B on the device: the parity tests on a build of the library with the defines."""
-    import build as simt_build
-    lib = simt_build.build(defines=defines, suffix=suffix)
-    for nodeid in nodeids:
-        run_pytest_on_emu(lib, nodeid)
-
-
 def run_worker(emu_lib, field, out, extra_env):
     env = dict(os.environ, SE_B200_LIB=emu_lib, **extra_env)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_simt_worker.py"), field, out], env=env, capture_output=True, text=True, timeout=600)
