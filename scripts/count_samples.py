@@ -7,7 +7,7 @@ from supereight_b200 import Map
 name = sys.argv[1] if len(sys.argv) > 1 else "planar_sweep_sdf512"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 cfg = bench.WORKLOADS[name]
-depth, poses, k = bench.make_frames(cfg, frames, seed=0)
+depth, poses, k = bench.make_frames(cfg, frames, 0)
 m = Map(cfg["field"], cfg["size"], cfg["dim"], cfg["W"], cfg["H"], max_blocks=cfg.get("max_blocks", 0))
 for f in range(frames):
     m.preprocess(depth[f]); m.integrate(poses[f], k, cfg["mu"], f)

@@ -3,7 +3,7 @@
   <round>_ncu_full_<workload>.csv        key metrics of the full captures, one row per launch
   <round>_sass_<workload>.txt            opcode mix / stall reasons of the hot kernels
   traffic.json                           dram bytes (read+write) per launch per stage, read by bench.py
-Usage: python scripts/summarise_profiles.py r1"""
+Usage: python scripts/summarise_profiles.py r2"""
 import collections
 import csv
 import json
@@ -12,12 +12,12 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 STAGE = {"k_mm2meters": "preprocess", "k_alloc_sdf": "alloc", "k_alloc_ofusion": "alloc", "k_alloc_first_key_chain": "alloc",
-         "k_active_list": "fuse", "k_integrate_sdf": "fuse", "k_integrate_ofusion": "fuse", "k_raycast": "raycast",
+         "k_integrate_sdf": "fuse", "k_integrate_ofusion": "fuse", "k_raycast": "raycast",
          "k_render_shade": "render", "k_render_volume": "render"}
 WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
@@ -44,7 +44,7 @@ def launches(workload):
     ours = {k: v for k, v in agg.items() if k.startswith("k_")}
     tot = sum(sum(v) for v in ours.values())
     with open(os.path.join(OUT, f"{R}_launches_{workload}.csv"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --workload %s --steps 4 --warmup 3\n" % workload)
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --workload %s --steps 4 --warmup 3 --no-cpu-baseline --no-extra\n" % workload)
         f.write("# per-launch times are cold-cache and serialised under ncu: compare the SHARES with bench.py's stage times, not the absolutes\n")
         f.write("kernel,launches,mean_us,total_us,share_of_our_kernels_pct\n")
         for k, v in sorted(ours.items(), key=lambda kv: -sum(kv[1])):
@@ -66,7 +66,7 @@ def full(workload, traffic):
     per_stage = collections.defaultdict(list)
     with open(os.path.join(OUT, f"{R}_ncu_full_{workload}.csv"), "w") as f:
         w = csv.writer(f)
-        f.write(f"# ncu --set full --clock-control none (cache control: flush before each replay) on scripts/profile_frames.py {workload}\n")
+        f.write(f"# ncu --set full --clock-control none (cache control: flush before each replay) on scripts/profile_frames.py {workload}: one frame's kernels at the bench's operating point (scripts/make_profiles.sh)\n")
         w.writerow(WANT)
         w.writerow([rows[1][i] if i >= 0 else "" for i in idx])
         for r in rows[2:]:
@@ -96,6 +96,7 @@ if os.path.exists(tp):
 for wl in ("planar_sweep_sdf512", "box_room_sdf2048", "box_room_ofusion1024"):
     launches(wl)
     full(wl, traffic)
-traffic["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over captured launches), summed over the kernels of a stage; from profiles/%s_ncu_full_*.csv" % R
+traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over captured launches), summed over the kernels of a stage; from profiles/%s_ncu_full_*.csv "
+                    "(one frame in the middle of the frames bench.py times: scripts/make_profiles.sh)" % R)
 json.dump(traffic, open(tp, "w"), indent=1, sort_keys=True)
 print(json.dumps(traffic, indent=1))

@@ -75,6 +75,7 @@ struct se_b200_map {
   // consumers of the float image).  pending_slot: the async-upload staging buffer it lives in, or -1.
   const unsigned short* pending_mm = nullptr;
   int pending_inW = 0, pending_ratio = 1, pending_slot = -1;
+  cudaEvent_t pending_upload = nullptr;   // the async upload that fills it (the converting stream waits for it), or nullptr
   int* d_active_list = nullptr;
   int* d_miss = nullptr;                  // SDF: directory cells of the blocks the allocation pass found missing (MissList)
   int miss_capacity = 0;
@@ -100,6 +101,13 @@ struct se_b200_map {
   int* h_status = nullptr;                // pinned + mapped: [0] = the allocation pass's error bits, written by the integrate kernel
   int* d_status = nullptr;                // its device alias
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  // Cross-frame overlap (SDF): the allocation pass of frame f+1 only reads the block directory and writes things the ray
+  // kernels never look at (float depth, active flags, the miss list) -- blocks are created later, inside the integrate
+  // kernel -- so it runs on a stream of its own, behind frame f's integrate kernel but BESIDE frame f's raycast / render.
+  cudaStream_t alloc_stream = nullptr;
+  cudaEvent_t ev_integrated = nullptr, ev_alloc_done = nullptr, ev_depth_ready = nullptr, ev_depth_read = nullptr;
+  bool integrated_valid = false, depth_ready_valid = false, depth_read_valid = false;   // integrated_valid: ev_integrated marks the LATEST integrate kernel
+  bool overlap_alloc = true;
   // overlapped host I/O (se_b200_*_host_async): the copy engines run on their own streams, double-buffered in HBM, tied
   // to the kernel stream by events, so frame N+1's upload and frame N's download overlap the kernels
   struct AsyncIo {
@@ -300,10 +308,11 @@ int report_pool_error(se_b200_map* m) {
 // image themselves)
 int resolve_depth(se_b200_map* m) {
   if (!m->pending_mm) return SE_B200_OK;
+  if (m->pending_upload) cudaStreamWaitEvent(m->stream, m->pending_upload, 0);
   dim3 block(32, 8), grid((m->W + 31) / 32, (m->H + 7) / 8);
   launch_pdl(k_mm2meters, grid, block, 0, m->stream, m->d_depth, m->pending_mm, m->W, m->H, m->pending_inW, m->pending_ratio);
   if (m->pending_slot >= 0) { cudaEventRecord(m->aio.consumed[m->pending_slot], m->stream); m->aio.consumed_valid[m->pending_slot] = true; }
-  m->pending_mm = nullptr; m->pending_slot = -1;
+  m->pending_mm = nullptr; m->pending_slot = -1; m->pending_upload = nullptr;
   return check_launch(m);
 }
 
@@ -351,8 +360,24 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   // a1 rides along: a pending millimetre image is converted by the allocation kernel's threads (one pixel each)
   DepthSource src;
   src.mm = m->pending_mm; src.inW = m->pending_inW; src.ratio = m->pending_ratio;
+  // SDF: the allocation kernel goes to the map's second stream, ordered behind the previous frame's integrate kernel (float
+  // depth, active flags, pools) and whatever still reads the float depth, but NOT behind that frame's raycast / render: it
+  // reads the block directory and creates nothing (se_b200_map::alloc_stream).  Per-stage timing keeps one stream.
+  // ... and not when the depth image itself arrives at the end of the main stream (se_b200_preprocess_depth_host's copy: the
+  // synchronous per-frame loop, where there is nothing to overlap with): stream order then does it all, and the launches
+  // keep their programmatic-dependent-launch edges (an event between two kernels breaks the edge).
+  const bool depth_on_main = m->pending_mm && m->depth_ready_valid;
+  const bool overlap = FieldTraits<V>::is_sdf && m->overlap_alloc && !m->stage_timing && !depth_on_main;
+  cudaStream_t as = overlap ? m->alloc_stream : m->stream;
+  if (overlap) {
+    if (!m->integrated_valid) { CUDA_TRY(cudaEventRecord(m->ev_integrated, m->stream)); m->integrated_valid = true; }   // (first frame / after a frame without overlap: everything so far)
+    CUDA_TRY(cudaStreamWaitEvent(as, m->ev_integrated, 0));
+    if (m->depth_read_valid) CUDA_TRY(cudaStreamWaitEvent(as, m->ev_depth_read, 0));
+  }
+  if (m->pending_mm && m->pending_upload) CUDA_TRY(cudaStreamWaitEvent(as, m->pending_upload, 0));
+  m->depth_read_valid = false; m->depth_ready_valid = false;
   if (FieldTraits<V>::is_sdf) {
-    launch_pdl(k_alloc_sdf<V>, grid_px, threads, 0, m->stream, view, m->d_depth, src, ap, miss, parity);
+    launch_pdl(k_alloc_sdf<V>, grid_px, threads, 0, as, view, m->d_depth, src, ap, miss, parity);
     if (int r = check_launch(m)) return r;
   } else {
     launch_pdl(k_alloc_ofusion<V>, grid_px, threads, 0, m->stream, view, m->d_depth, src, ap, m->d_requests, m->max_requests);
@@ -360,8 +385,12 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
     if (int r = check_launch(m, 2)) return r;
   }
   if (m->pending_mm) {
-    if (m->pending_slot >= 0) { CUDA_TRY(cudaEventRecord(m->aio.consumed[m->pending_slot], m->stream)); m->aio.consumed_valid[m->pending_slot] = true; }
-    m->pending_mm = nullptr; m->pending_slot = -1;
+    if (m->pending_slot >= 0) { CUDA_TRY(cudaEventRecord(m->aio.consumed[m->pending_slot], as)); m->aio.consumed_valid[m->pending_slot] = true; }
+    m->pending_mm = nullptr; m->pending_slot = -1; m->pending_upload = nullptr;
+  }
+  if (overlap) {
+    CUDA_TRY(cudaEventRecord(m->ev_alloc_done, as));
+    CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_alloc_done, 0));
   }
   stage_end(m, SE_B200_STAGE_ALLOC);
 
@@ -391,30 +420,25 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
     }
     m->grid_integrate = m->num_sms * occ;
   }
-  // A/B: the list (and the deferred block creation) in a kernel of its own instead of inside the integrate kernel
-  static const bool list_kernel = [] { const char* e = std::getenv("SE_B200_LIST_KERNEL"); return e && e[0] == '1'; }();
-  int* status = m->d_status;
-  if (list_kernel) {
-    launch_pdl(k_prepare_blocks<V>, m->num_sms * 2, kListThreads, 0, m->stream, view, fp, m->d_active_list, miss, parity, status);
-    if (int r = check_launch(m)) return r;
-    status = nullptr;
-  }
   // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
   // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
   bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
   for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
   if (FieldTraits<V>::is_sdf) {
-    if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status);
-    else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status);
+    if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status);
+    else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status);
   } else {
     // check-free sequences + tabulated log-odds increment: the default (fuse 130 -> 59 us on box_room_ofusion1024,
     // same bits); SE_B200_OFUSION_FAST=0 or SE_B200_IEEE_DIV select the instantiation with the plain operators
     const char* e = std::getenv("SE_B200_OFUSION_FAST");
     const bool ofusion_fast = !(e && e[0] == '0');
-    if (fast && ofusion_fast && m->d_logodds) launch_pdl(k_integrate_ofusion<true>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status, (const float*)m->d_logodds);
-    else launch_pdl(k_integrate_ofusion<false>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, status, (const float*)m->d_logodds);
+    if (fast && ofusion_fast && m->d_logodds) launch_pdl(k_integrate_ofusion<true>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status, (const float*)m->d_logodds);
+    else launch_pdl(k_integrate_ofusion<false>, m->grid_integrate, threads, 0, m->stream, m->view<OfuVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status, (const float*)m->d_logodds);
   }
   if (int r = check_launch(m, 1)) return r;
+  // the next frame's allocation kernel may start from here on -- recorded only while frames do overlap
+  if (overlap) CUDA_TRY(cudaEventRecord(m->ev_integrated, m->stream));
+  m->integrated_valid = overlap;
   stage_end(m, SE_B200_STAGE_FUSE);
   return SE_B200_OK;
 }
@@ -660,6 +684,12 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
 #define CREATE_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { fail(SE_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); return cleanup(SE_B200_ERR_CUDA); } } while (0)
   CREATE_TRY(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
   m->stream = m->own_stream;
+  CREATE_TRY(cudaStreamCreateWithFlags(&m->alloc_stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreateWithFlags(&m->ev_integrated, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&m->ev_alloc_done, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&m->ev_depth_ready, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&m->ev_depth_read, cudaEventDisableTiming));
+  { const char* e = std::getenv("SE_B200_NO_ALLOC_OVERLAP"); m->overlap_alloc = !(e && e[0] == '1'); }
   for (int i = 0; i < SE_B200_NUM_STAGES; ++i) { CREATE_TRY(cudaEventCreate(&m->ev_begin[i])); CREATE_TRY(cudaEventCreate(&m->ev_end[i])); }
   CREATE_TRY(cudaMallocHost(&m->h_counters, kNumCounters * sizeof(int)));
   CREATE_TRY(cudaHostAlloc(&m->h_status, 4 * sizeof(int), cudaHostAllocMapped));
@@ -717,6 +747,11 @@ int se_b200_destroy(se_b200_map* m) {
     }
     cudaStreamDestroy(m->aio.up); cudaStreamDestroy(m->aio.down);
   }
+  if (m->alloc_stream) { cudaStreamSynchronize(m->alloc_stream); cudaStreamDestroy(m->alloc_stream); }
+  if (m->ev_integrated) cudaEventDestroy(m->ev_integrated);
+  if (m->ev_alloc_done) cudaEventDestroy(m->ev_alloc_done);
+  if (m->ev_depth_ready) cudaEventDestroy(m->ev_depth_ready);
+  if (m->ev_depth_read) cudaEventDestroy(m->ev_depth_read);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   cudaGetLastError();
   delete m;
@@ -727,6 +762,8 @@ int se_b200_set_stream(se_b200_map* m, void* s) {
   REQUIRE_MAP(m);
   DeviceGuard guard(m->device);
   CUDA_TRY(cudaStreamSynchronize(m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->alloc_stream));
+  m->integrated_valid = m->depth_ready_valid = m->depth_read_valid = false;
   m->stream = s ? (cudaStream_t)s : m->own_stream;
   for (bool& v : m->ev_valid) v = false;
   return SE_B200_OK;
@@ -736,15 +773,16 @@ int se_b200_sync(se_b200_map* m) {
   REQUIRE_MAP(m);
   DeviceGuard guard(m->device);
   CUDA_TRY(cudaStreamSynchronize(m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->alloc_stream));
   if (m->aio.ready) { CUDA_TRY(cudaStreamSynchronize(m->aio.up)); CUDA_TRY(cudaStreamSynchronize(m->aio.down)); }
   return SE_B200_OK;
 }
 
 // a1 is deferred: remember where the millimetre image is; the allocation kernel of the next integrate converts it
 // (resolve_depth() does for any other consumer of the float image)
-static int preprocess_common(se_b200_map* m, const uint16_t* src_dev, int inW, int inH, int slot) {
+static int preprocess_common(se_b200_map* m, const uint16_t* src_dev, int inW, int inH, int slot, cudaEvent_t upload) {
   (void)inH;
-  m->pending_mm = src_dev; m->pending_inW = inW; m->pending_ratio = inW / m->W; m->pending_slot = slot;
+  m->pending_mm = src_dev; m->pending_inW = inW; m->pending_ratio = inW / m->W; m->pending_slot = slot; m->pending_upload = upload;
   return SE_B200_OK;
 }
 static int check_ratio(se_b200_map* m, int inW, int inH) {
@@ -786,7 +824,8 @@ int se_b200_preprocess_depth_host(se_b200_map* m, const uint16_t* depth_mm, int 
   }
   stage_begin(m, SE_B200_STAGE_PREPROCESS);
   CUDA_TRY(cudaMemcpyAsync(m->d_depth_mm, depth_mm, bytes, cudaMemcpyHostToDevice, m->stream));
-  if (int r = preprocess_common(m, m->d_depth_mm, inW, inH, -1)) return r;
+  CUDA_TRY(cudaEventRecord(m->ev_depth_ready, m->stream)); m->depth_ready_valid = true;      // (the allocation kernel may run on another stream)
+  if (int r = preprocess_common(m, m->d_depth_mm, inW, inH, -1, nullptr)) return r;
   stage_end(m, SE_B200_STAGE_PREPROCESS);
   return SE_B200_OK;
 }
@@ -797,7 +836,8 @@ int se_b200_preprocess_depth_device(se_b200_map* m, const uint16_t* depth_mm_dev
   if (int r = check_ratio(m, inW, inH)) return r;
   DeviceGuard guard(m->device);
   stage_begin(m, SE_B200_STAGE_PREPROCESS);
-  if (int r = preprocess_common(m, depth_mm_dev, inW, inH, -1)) return r;
+  m->depth_ready_valid = false;
+  if (int r = preprocess_common(m, depth_mm_dev, inW, inH, -1, nullptr)) return r;
   stage_end(m, SE_B200_STAGE_PREPROCESS);
   return SE_B200_OK;
 }
@@ -835,9 +875,9 @@ int se_b200_preprocess_depth_host_async(se_b200_map* m, const uint16_t* depth_mm
   if (a.consumed_valid[s]) CUDA_TRY(cudaStreamWaitEvent(a.up, a.consumed[s], 0));      // the frame two calls ago has read this buffer
   CUDA_TRY(cudaMemcpyAsync(a.d_mm[s], depth_mm, bytes, cudaMemcpyHostToDevice, a.up));
   CUDA_TRY(cudaEventRecord(a.uploaded[s], a.up));
-  CUDA_TRY(cudaStreamWaitEvent(m->stream, a.uploaded[s], 0));
+  m->depth_ready_valid = false;
   stage_begin(m, SE_B200_STAGE_PREPROCESS);
-  if (int r = preprocess_common(m, a.d_mm[s], inW, inH, s)) return r;      // `consumed[s]` is recorded by whoever converts the image
+  if (int r = preprocess_common(m, a.d_mm[s], inW, inH, s, a.uploaded[s])) return r;      // whoever converts the image waits for the upload and records `consumed[s]`
   stage_end(m, SE_B200_STAGE_PREPROCESS);
   return SE_B200_OK;
 }
@@ -972,6 +1012,7 @@ int se_b200_render_depth_host(se_b200_map* m, uint8_t* out) {
   if (int r = resolve_depth(m)) return r;
   k_render_depth<<<(n + 255) / 256, 256, 0, m->stream>>>(m->d_rgba, m->d_depth, n, kNearPlane, kFarPlane);
   if (int r = check_launch(m)) return r;
+  CUDA_TRY(cudaEventRecord(m->ev_depth_read, m->stream)); m->depth_read_valid = true;      // (the next allocation kernel overwrites the float depth from another stream)
   CUDA_TRY(cudaMemcpyAsync(out, m->d_rgba, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return SE_B200_OK;
@@ -1303,6 +1344,7 @@ int se_b200_filter_depth(se_b200_map* m, int filter, int levels) {
   } else {
     CUDA_TRY(cudaMemcpyAsync(m->d_scaled_depth[0], m->d_depth, (size_t)m->W * m->H * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
   }
+  CUDA_TRY(cudaEventRecord(m->ev_depth_read, m->stream)); m->depth_read_valid = true;
   return SE_B200_OK;
 }
 

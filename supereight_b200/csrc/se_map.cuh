@@ -112,17 +112,20 @@ __device__ __forceinline__ bool in_volume(const MapView<V>& m, int x, int y, int
 // outside the volume read as "not allocated" (the reference indexes out of bounds there).
 // Read-only accessors (this one, get_fine, interp, grad) go through the non-coherent cache
 // (__ldg): they are only used by kernels that do not modify the tree.
-// the tree descent itself, kept out of line: with the directory it is only the fallback
-template <class V>
-__device__ __noinline__ int fetch_block_tree(const MapView<V>& m, int x, int y, int z) {
+// the tree descent itself, kept out of line: with the directory it is only the fallback.  (The out-of-line helpers of this
+// file take what they need BY VALUE: a reference to the kernel's MapView parameter would force every thread to copy the
+// whole 140-byte struct to local memory at kernel entry -- 17 STL.64 per thread in the round-1 kernels.)
+__device__ __noinline__ int fetch_block_tree_impl(const int* __restrict__ node_child, int size, int x, int y, int z) {
   int n = 0;
-  for (int edge = m.size >> 1; edge >= kBlockSide; edge >>= 1) {
+  for (int edge = size >> 1; edge >= kBlockSide; edge >>= 1) {
     const int slot = ((x & edge) != 0) | (((y & edge) != 0) << 1) | (((z & edge) != 0) << 2);
-    n = __ldg(m.node_child + 8 * n + slot);
+    n = __ldg(node_child + 8 * n + slot);
     if (n < 0) return kEmpty;
   }
   return n;
 }
+template <class V>
+__device__ __forceinline__ int fetch_block_tree(const MapView<V>& m, int x, int y, int z) { return fetch_block_tree_impl(m.node_child, m.size, x, y, z); }
 template <class V>
 __device__ __forceinline__ int fetch_block(const MapView<V>& m, int x, int y, int z) {
   if (!in_volume(m, x, y, z)) return kEmpty;
@@ -277,7 +280,7 @@ __device__ __forceinline__ float trilinear(const float (&p)[8], float fx, float 
 }
 // positions on the volume's faces / maps without the directory: out of line (rays almost never sample there)
 template <class V>
-__device__ __noinline__ float interp_field_general(const MapView<V>& m, int bx, int by, int bz, float fx, float fy, float fz) {
+__device__ __noinline__ float interp_field_general(const MapView<V> m, int bx, int by, int bz, float fx, float fy, float fz) {
   float p[8];
   gather_points_general(m, bx, by, bz, p);
   return trilinear(p, fx, fy, fz);
@@ -345,7 +348,7 @@ __device__ __forceinline__ V3 grad_blend(const float (&g)[kGradSamples], float w
 // and then reads out of bounds; here such a sample reads initValue(), like get_fine on an unallocated block)
 // and for pools too large for 32-bit voxel indices.  Out of line: rays almost never end there.
 template <class V>
-__device__ __noinline__ V3 grad_field_general(const MapView<V>& m, int b0, int b1, int b2, float wx1, float wy1, float wz1, float scale) {
+__device__ __noinline__ V3 grad_field_general(const MapView<V> m, int b0, int b1, int b2, float wx1, float wy1, float wz1, float scale) {
   float g[kGradSamples];
   const int hi = m.size - 1;
   const int x4[4] = { max(b0 - 1, 0), max(b0, 0), min(b0 + 1, hi), min(b0 + 2, hi) };

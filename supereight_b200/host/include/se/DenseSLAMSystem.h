@@ -114,6 +114,14 @@ class DenseSLAMSystem {
   // extension (se_b200_set_render_target): raycasting() also renders the reuse-path image into `out` (device memory or
   // page-locked host memory, W*H*4 bytes; nullptr turns it off); renderVolume(out, ...) with the same pointer then only waits
   void setRenderTarget(unsigned char* out);
+  // page-lock a caller-owned host buffer (se_b200_register_host_buffer): the reference application malloc()s its depth and
+  // RGBA buffers (se_apps/src/benchmark.cpp:90-97), which makes every transfer a staged synchronous copy; registered once,
+  // preprocessing() uploads asynchronously and renderVolume() / the render target write the image in place.  Unregister
+  // before the memory is freed.
+  static void registerHostBuffer(void* ptr, size_t bytes);
+  static void unregisterHostBuffer(void* ptr);
+  // per-stage device timing for stageMilliseconds() (off by default: the event records cost ~10 % of a frame)
+  void enableStageTiming(bool on);
   // device time of the last run of a stage in ms (stands in for the TICK/TOCK samples, se_shared/timings.h)
   float stageMilliseconds(int stage);
   se_b200_map* handle() { return map_; }

@@ -10,6 +10,7 @@
 #include <type_traits>
 
 #include "se_b200.h"
+#include <iostream>
 
 namespace {
 constexpr int kFieldType = std::is_same<FieldType, SDF>::value ? SE_B200_SDF : SE_B200_OFUSION;
@@ -218,6 +219,12 @@ void DenseSLAMSystem::getVertexNormal(std::vector<float>& vertex, std::vector<fl
 void DenseSLAMSystem::setRenderTarget(unsigned char* out) {
   SE_CHECK(se_b200_set_render_target(map_, out), "setRenderTarget");
 }
+
+void DenseSLAMSystem::registerHostBuffer(void* ptr, size_t bytes) {
+  if (se_b200_register_host_buffer(ptr, bytes) != SE_B200_OK) { std::cerr << "DenseSLAMSystem: " << se_b200_last_error() << std::endl; exit(1); }
+}
+void DenseSLAMSystem::unregisterHostBuffer(void* ptr) { se_b200_unregister_host_buffer(ptr); }
+void DenseSLAMSystem::enableStageTiming(bool on) { SE_CHECK(se_b200_set_stage_timing(map_, on ? 1 : 0), "enableStageTiming"); }
 
 float DenseSLAMSystem::stageMilliseconds(int stage) {
   float ms = 0.f;

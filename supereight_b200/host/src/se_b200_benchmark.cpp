@@ -104,6 +104,12 @@ int main(int argc, char** argv) {
   std::vector<unsigned char> depthRender((size_t)cw * ch * 4), trackRender((size_t)cw * ch * 4), volumeRender((size_t)cw * ch * 4);
 
   DenseSLAMSystem pipeline(Eigen::Vector2i(cw, ch), config.volume_resolution, config.volume_size, init_pose, config.pyramid, config);
+  // The reference's driver malloc()s these buffers (benchmark.cpp:90-97).  Page-locked once, the depth upload is an
+  // asynchronous DMA and the images are written in place; with an image wanted every frame the raycast kernel renders
+  // straight into volumeRender (setRenderTarget) and renderVolume() only waits for it.
+  DenseSLAMSystem::registerHostBuffer(inputDepth.data(), inputDepth.size() * sizeof(uint16_t));
+  for (auto* v : {&depthRender, &trackRender, &volumeRender}) DenseSLAMSystem::registerHostBuffer(v->data(), v->size());
+  if (config.rendering_rate == 1) pipeline.setRenderTarget(volumeRender.data());
 
   using clk = std::chrono::steady_clock;
   std::chrono::time_point<clk> t[7];
@@ -185,5 +191,8 @@ int main(int argc, char** argv) {
       put(os, vertex); put(os, normal);
     }
   }
+  pipeline.setRenderTarget(nullptr);
+  DenseSLAMSystem::unregisterHostBuffer(inputDepth.data());
+  for (auto* v : {&depthRender, &trackRender, &volumeRender}) DenseSLAMSystem::unregisterHostBuffer(v->data());
   return 0;
 }

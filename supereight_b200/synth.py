@@ -8,7 +8,7 @@ SURVEY.md section 8(d) "Concrete synthetic inputs":
 Depth is the exact z-depth of the ray through the pixel centre (integer pixel coordinates, the
 convention of the reference's raycast, rendering.cpp:63), rounded to uint16 millimetres, which is
 what the reference's readers hand to DenseSLAMSystem::preprocessing.  Optional Gaussian noise
-(sigma 2 mm, MT19937 seed 1234) and 1 % drop-outs (seed 4321) exercise the depth==0 paths.
+(sigma 2 mm, MT19937 seed 1234 + g for sequence g) and 1 % drop-outs (seed 4321 + g) exercise the depth==0 paths.
 
 Pure numpy, deterministic, no GPU: inputs only -- not part of the oracle and not a compute path.
 """
@@ -40,14 +40,17 @@ def _rays(W: int, H: int, k, pose: np.ndarray):
 
 
 def _finish(depth_m: np.ndarray, frame: int, noise_mm: float, dropout: float, seed: int) -> np.ndarray:
+    """`seed` = g, the index of the sequence (BASELINE.json config 5: "seeds 1234+g"): its noise comes from MT19937 seeded
+    1234 + g and its drop-outs from MT19937 seeded 4321 + g, one independent sub-stream per frame (SeedSequence spawn key =
+    the frame number), so frames can be generated in any order."""
     d = depth_m * 1000.0
     if noise_mm > 0:
-        rng = np.random.Generator(np.random.MT19937(1234 + seed * 7919 + frame))
+        rng = np.random.Generator(np.random.MT19937(np.random.SeedSequence(1234 + seed, spawn_key=(frame,))))
         d = d + rng.normal(0.0, noise_mm, size=d.shape)
     d = np.where(np.isfinite(d) & (d > 0) & (d < 65535), d, 0.0)
     out = np.rint(d).astype(np.uint16)
     if dropout > 0:
-        rng = np.random.Generator(np.random.MT19937(4321 + seed * 104729 + frame))
+        rng = np.random.Generator(np.random.MT19937(np.random.SeedSequence(4321 + seed, spawn_key=(frame,))))
         out[rng.random(out.shape) < dropout] = 0
     return np.ascontiguousarray(out)
 

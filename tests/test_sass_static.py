@@ -77,8 +77,8 @@ def test_register_budgets(resources):
     # (template arguments: field, DENSE walk, COUNT, SHADE)
     ray = [n for n in resources if n.startswith("k_raycast<")]
     assert len(ray) >= 8, ray
-    for name in ray:
-        assert resources[name]["REG"] <= 64 and resources[name]["STACK"] <= 256, (name, resources[name])
+    for name in ray:      # (no frame: the out-of-line slow paths take the map by value, not the kernel parameter by reference)
+        assert resources[name]["REG"] <= 64 and resources[name]["STACK"] <= 64, (name, resources[name])
     # integrate (SDF): 4 CTAs x 256 threads per SM -> <= 64 registers, no stack; its 32 KiB of half-block stage buffers are dynamic smem
     for name in ("k_integrate_sdf<true>", "k_integrate_sdf<false>"):
         assert resources[name]["REG"] <= 64 and resources[name]["STACK"] == 0, (name, resources[name])
@@ -87,7 +87,7 @@ def test_register_budgets(resources):
     for name, stack in (("k_integrate_ofusion<true>", 0), ("k_integrate_ofusion<false>", 16)):
         assert resources[name]["REG"] <= 64 and resources[name]["STACK"] <= stack, (name, resources[name])
     # allocation: 5 CTAs x 256 threads -> <= 51, the per-thread block lists live in (static) shared memory
-    assert resources["k_alloc_sdf<SdfVoxel>"]["REG"] <= 51 and resources["k_alloc_sdf<SdfVoxel>"]["STACK"] <= 64
+    assert resources["k_alloc_sdf<SdfVoxel>"]["REG"] <= 51 and resources["k_alloc_sdf<SdfVoxel>"]["STACK"] == 0
     assert resources["k_alloc_ofusion<OfuVoxel>"]["REG"] <= 64 and resources["k_alloc_ofusion<OfuVoxel>"]["STACK"] == 0
 
 
