@@ -136,6 +136,7 @@ struct se_b200_map {
   template <class V> MapView<V> view() const {
     MapView<V> v;
     v.size = size; v.dim = dim; v.max_level = max_level; v.leaves_level = leaves_level;
+    v.inv_voxel = (float)size / dim; v.grad_scale = (0.5f * dim) / (float)size;
     v.max_nodes = max_nodes; v.max_blocks = max_blocks;
     v.node_child = p.node_child; v.node_code = p.node_code; v.node_side = p.node_side; v.node_mask = p.node_mask;
     v.node_value = (V*)p.node_value;

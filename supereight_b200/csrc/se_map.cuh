@@ -58,6 +58,10 @@ template <> struct FieldTraits<OfuVoxel> {
 template <class V> struct MapView {
   int size;            // voxels per side
   float dim;           // metres per side
+  // (float)size / dim and (0.5f * dim) / (float)size: the metres -> voxels factor of VolumeTemplate::{get,interp,grad}
+  // (volume_template.hpp:77-102) and the gradient's scale (octree.hpp:735), each ONE correctly rounded division that is the
+  // same for every sample -- computed once on the host (se_b200_map::view) instead of per call on the device
+  float inv_voxel, grad_scale;
   int max_level;       // log2(size)
   int leaves_level;    // max_level - 3
   int max_nodes, max_blocks;
@@ -266,7 +270,7 @@ __device__ __forceinline__ void gather_points(const MapView<V>& m, BlockCache& c
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int off = xo[i & 1] + yo[(i >> 1) & 1] + zo[(i >> 2) & 1];
-    const int b = i == 0 ? id0 : (id[i] < 0 ? m.max_blocks : id[i]);
+    const int b = i == 0 ? id0 : (int)min((unsigned)id[i], (unsigned)m.max_blocks);      // kEmpty (-1) -> the initValue() payload
     p[i] = load_x(m.block_data + (size_t)b * kBlockVoxels + off);
   }
 }
@@ -382,7 +386,7 @@ template <class V>
 __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*threads*/ 128], V3 pos) {
   const float flx = floorf(pos.x), fly = floorf(pos.y), flz = floorf(pos.z);
   const int b0 = (int)flx, b1 = (int)fly, b2 = (int)flz;
-  const float scale = (0.5f * m.dim) / (float)m.size;
+  const float scale = m.grad_scale;
   const int hi = m.size - 1;
   // every clamped coordinate inside [0, hi]  <=>  -1 <= b <= hi on each axis
   const bool inside = ((unsigned)(b0 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b1 + 1) <= (unsigned)(hi + 1)) & ((unsigned)(b2 + 1) <= (unsigned)(hi + 1));
@@ -463,19 +467,23 @@ __device__ __forceinline__ V3 grad_field(const MapView<V>& m, int2 (*pairs)[/*th
 template <class V>
 __device__ __forceinline__ V vol_get(const MapView<V>& m, BlockCache& c, V3 p) {
   c.n_get++;
-  const float inv = (float)m.size / m.dim;
+  const float inv = m.inv_voxel;
   return get_fine(m, c, (int)(inv * p.x), (int)(inv * p.y), (int)(inv * p.z));
 }
 template <class V>
 __device__ __forceinline__ float vol_interp(const MapView<V>& m, BlockCache& c, V3 p) {
   c.n_interp++;
-  const float inv = (float)m.size / m.dim;
+  const float inv = m.inv_voxel;
   return interp_field(m, c, v3(inv * p.x, inv * p.y, inv * p.z));
 }
+// (Measured on the device, round 2: issuing get(p)'s load and the eight corner loads interp(p) may need right after it in ONE
+// round -- the march of raycast() calls both at the same point -- LOSES: raycast 32.6 -> 35.8 us at 512^3, 172 -> 198 us
+// for OFusion 1024^3.  The extra address arithmetic and loads of the samples that need no interpolation cost more than
+// the saved round trip.)
 template <class V>
 __device__ __forceinline__ V3 vol_grad(const MapView<V>& m, BlockCache& c, int2 (*ids)[128], V3 p) {
   c.n_grad++;
-  const float inv = (float)m.size / m.dim;
+  const float inv = m.inv_voxel;
   return grad_field(m, ids, v3(inv * p.x, inv * p.y, inv * p.z));
 }
 

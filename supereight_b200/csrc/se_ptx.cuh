@@ -20,9 +20,11 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 // ---- inter-warp hand-off through global memory (the integrate kernels' in-kernel active list) --------
-// acquire load of a counter another warp releases with __threadfence() + atomicAdd; the poll backs off with nanosleep
-__device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// ld_relaxed: a coherent (L2) load for polling.  NOT ld.acquire: ptxas implements an acquire at gpu scope with CCTL.IVALL --
+// an invalidation of the SM's whole L1 -- and a polling loop made of those wiped the depth image out of L1 twenty thousand
+// times per launch (ncu, round 2: 20 % of the integrate kernel's stall samples sat on CCTL).  What a poll guards is read
+// through L2 as well (block_coord via __ldcg, the payload by the TMA engine), so no acquire is needed.
+__device__ __forceinline__ int ld_relaxed(const int* p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void poll_backoff() { asm volatile("nanosleep.u32 64;" ::: "memory"); }
 
 // ---- predicated read-only load: `pred ? __ldg(p) : otherwise` as one predicated LDG, never a branch ----

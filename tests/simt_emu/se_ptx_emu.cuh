@@ -13,8 +13,7 @@ namespace se_b200 {
 
 __device__ __forceinline__ void pdl_prologue() {}
 
-__device__ __forceinline__ int ld_acquire(const int* p) { return *(const volatile int*)p; }
-__device__ __forceinline__ void st_release(int* p, int v) { *(volatile int*)p = v; }
+__device__ __forceinline__ int ld_relaxed(const int* p) { return *(const volatile int*)p; }
 __device__ __forceinline__ void poll_backoff() { simt::yield(); }
 
 __device__ __forceinline__ int ldg_if(bool pred, const int* p, int otherwise) { return pred ? *p : otherwise; }
