@@ -17,6 +17,7 @@ PerfStats Stats;                       // the application defines it in the refe
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -43,6 +44,8 @@ extern "C" {
 
 int seo_ref_field() { return kField; }
 
+// SEO_REF_PYRAMID_LEVELS (environment, read at creation): pyramid depth of the pipelines created afterwards; default: the 3
+// levels {10, 5, 4} of the reference's default configuration
 void* seo_create(int field, int size, float dim, int W, int H) {
   if (field != kField) return nullptr;
   Handle* h = new Handle;
@@ -50,6 +53,7 @@ void* seo_create(int field, int size, float dim, int W, int H) {
   Configuration config;
   config.mu = 0.1f;
   std::vector<int> pyramid = {10, 5, 4};
+  if (const char* e = std::getenv("SEO_REF_PYRAMID_LEVELS")) pyramid.assign((size_t)std::max(1, std::atoi(e)), 4);
   Eigen::Matrix4f init = Eigen::Matrix4f::Identity();
   h->sys = new DenseSLAMSystem(Eigen::Vector2i(W, H), Eigen::Vector3i::Constant(size), Eigen::Vector3f::Constant(dim), init, pyramid, config);
   return h;

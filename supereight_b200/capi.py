@@ -262,6 +262,12 @@ class Map:
         self._check(self.lib.se_b200_block_count(self.h, C.byref(n)))
         return n.value
 
+    def block_count_nothrow(self):
+        """the count even when the call reports SE_B200_ERR_POOL (the value is filled in before the status is returned)"""
+        n = C.c_int()
+        self.lib.se_b200_block_count(self.h, C.byref(n))
+        return n.value
+
     def node_count(self):
         n = C.c_int()
         self._check(self.lib.se_b200_node_count(self.h, C.byref(n)))

@@ -389,6 +389,17 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
     if (m->pending_slot >= 0) { CUDA_TRY(cudaEventRecord(m->aio.consumed[m->pending_slot], as)); m->aio.consumed_valid[m->pending_slot] = true; }
     m->pending_mm = nullptr; m->pending_slot = -1; m->pending_upload = nullptr;
   }
+  const M4 Tcw = rigid_inverse(pose);
+  const M4 K = camera_matrix(k);
+  FrustumParams fp;
+  fp.cam = mul44(K, Tcw);
+  fp.voxelSize = voxelsize; fp.W = m->W; fp.H = m->H;
+  // a8 for the blocks that existed before the frame: behind the allocation kernel on its stream (SDF; see k_filter_blocks)
+  const int prefiltered = FieldTraits<V>::is_sdf ? 1 : 0;
+  if (prefiltered) {
+    launch_pdl(k_filter_blocks<V>, m->num_sms * 2, kListThreads, 0, as, view, fp, m->d_active_list, parity);
+    if (int r = check_launch(m)) return r;
+  }
   if (overlap) {
     CUDA_TRY(cudaEventRecord(m->ev_alloc_done, as));
     CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_alloc_done, 0));
@@ -396,11 +407,6 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   stage_end(m, SE_B200_STAGE_ALLOC);
 
   stage_begin(m, SE_B200_STAGE_FUSE);
-  const M4 Tcw = rigid_inverse(pose);
-  const M4 K = camera_matrix(k);
-  FrustumParams fp;
-  fp.cam = mul44(K, Tcw);
-  fp.voxelSize = voxelsize; fp.W = m->W; fp.H = m->H;
   IntegrateParams ip;
   ip.Tcw = Tcw; ip.K = K;
   ip.delta = rot3(Tcw, v3(voxelsize, 0.f, 0.f));
@@ -426,8 +432,8 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
   for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
   if (FieldTraits<V>::is_sdf) {
-    if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status);
-    else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status);
+    if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status, prefiltered);
+    else launch_pdl(k_integrate_sdf<false>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status, prefiltered);
   } else {
     // check-free sequences + tabulated log-odds increment: the default (fuse 130 -> 59 us on box_room_ofusion1024,
     // same bits); SE_B200_OFUSION_FAST=0 or SE_B200_IEEE_DIV select the instantiation with the plain operators

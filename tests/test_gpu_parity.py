@@ -333,6 +333,34 @@ def test_error_paths_and_render_track():
         small.block_count()
 
 
+def test_pool_exhaustion_surfaces_from_the_per_frame_calls():
+    """A caller that only drives the stages (the DenseSLAMSystem shim never asks for counters) still learns that a pool ran
+    out: the frame's integrate kernel hands the error bits to the host, and a later se_b200_integrate / se_b200_raycast returns
+    SE_B200_ERR_POOL -- once; the condition is cleared, and the map keeps working with what fitted."""
+    from supereight_b200 import Map, SeB200Error, synth
+    k = scaled_k(160)
+    small = Map(SDF, 256, 4.8, 160, 120, max_blocks=16)
+    raised = 0
+    for f in range(6):
+        d, pose = synth.planar_sweep(f, 4.8, 160, 120, k)
+        small.preprocess(d)
+        for call in (lambda: small.integrate(pose, k, 0.1, f), lambda: small.raycast(pose, k, 0.1)):
+            try:
+                call()
+            except SeB200Error as e:
+                assert "pool exhausted" in str(e)
+                raised += 1
+        small.sync()                      # (the per-frame calls do not wait for the device; give the flag time to arrive)
+    assert raised >= 1
+    # the pool stays full, so every frame raises the condition anew; a map with room never reports anything
+    assert small.block_count_nothrow() == 16
+    big = Map(SDF, 256, 4.8, 160, 120)
+    for f in range(3):
+        d, pose = synth.planar_sweep(f, 4.8, 160, 120, k)
+        big.preprocess(d); big.integrate(pose, k, 0.1, f); big.raycast(pose, k, 0.1); big.sync()
+    assert big.block_count() > 16
+
+
 @pytest.mark.parametrize("field,mu", [(SDF, 0.1), (OFUSION, 0.008)])
 def test_map_export_import_round_trip(field, mu):
     """Octree::save -> Octree::load (octree.hpp:897-950) through the ABI: a map rebuilt from its exported records

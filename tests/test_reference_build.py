@@ -101,3 +101,26 @@ def test_gtest_standin_reports_failures(tmp_path):
     assert "[  PASSED  ] 1 tests." in r.stdout and "[  FAILED  ] 2 tests." in r.stdout
     assert "UNREACHED" not in r.stdout and "CONTINUED" in r.stdout and "msg" in r.stdout
 
+
+
+def test_half_sample_pyramid_with_odd_level_widths(monkeypatch):
+    """halfSampleRobustImageKernel indexes its input with in.width() (preprocessing.cpp:209,217): at 100 x 76 the pyramid is
+    100 / 50 / 25 / 12 wide and level 3 reads a parent whose row stride (25) is not twice its own width (the reference
+    accepts it: 25 / 12 == 2 in integer arithmetic).  Oracle and reference build, four levels, bit for bit."""
+    import numpy as np
+    from oracle_lib import SDF, Oracle
+    from supereight_b200 import synth
+    monkeypatch.setenv("SEO_REF_PYRAMID_LEVELS", "4")
+    W, H, dim = 100, 76, 4.8
+    k = tuple(v * W / 640.0 for v in synth.DEFAULT_K)
+    o, r = Oracle(SDF, 128, dim, W, H), Oracle(SDF, 128, dim, W, H, kind="ref_sdf")
+    d, pose = synth.corner_view(2, dim, W, H, k, noise_mm=2.0, dropout=0.01)
+    for p in (o, r):
+        assert p.preprocess(d) == 0
+        p.filter_depth(True, 4)
+        p.track(pose, pose, k, 1e-5, [0, 0, 0, 0])           # builds the pyramid and the per-level vertex / normal maps, no ICP iteration
+    for lvl in range(4):
+        od, ov, on = o.pyramid(lvl); rd, rv, rn = r.pyramid(lvl)
+        assert od.shape == (H >> lvl, W >> lvl)
+        assert od.tobytes() == rd.tobytes() and ov.tobytes() == rv.tobytes() and on.tobytes() == rn.tobytes(), lvl
+    assert (o.pyramid(3)[0] > 0).mean() > 0.5

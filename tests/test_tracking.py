@@ -153,3 +153,25 @@ def test_cuda_tracking_follows_a_sequence():
             assert ok
             assert np.abs(est[:3, 3] - gt[:3, 3]).max() < 0.03            # ~1.5 voxels of drift at 19 mm voxels
         g.integrate(est, K, MU, f); g.raycast(est, K, MU); rp = est.copy()
+
+
+@pytest.mark.gpu
+def test_cuda_pyramid_with_odd_level_widths():
+    """100 x 76 with four levels: 100 / 50 / 25 / 12 -- level 3 halves a 25-wide parent, whose row stride is not twice the
+    child's width (halfSampleRobustImageKernel indexes with in.width(), preprocessing.cpp:209,217).  Device == oracle (and
+    the oracle == the reference build there: tests/test_reference_build.py)."""
+    from supereight_b200 import Map
+    w, h = 100, 76
+    k = tuple(v * w / 640.0 for v in synth.DEFAULT_K)
+    g, o = Map(SDF, 128, DIM, w, h), Oracle(SDF, 128, DIM, w, h)
+    d, pose = synth.corner_view(2, DIM, w, h, k, noise_mm=2.0, dropout=0.01)
+    for p in (g, o):
+        p.preprocess(d); p.filter_depth(True, 4)
+        p.track(pose, pose, k, 1e-5, [0, 0, 0, 0])
+    for lvl in range(4):
+        gd, gv, gn = g.pyramid(lvl); od, ov, on = o.pyramid(lvl)
+        assert gd.shape == (h >> lvl, w >> lvl)
+        np.testing.assert_allclose(gd, od, rtol=2e-6, atol=1e-7)            # expf: device vs libm
+        np.testing.assert_allclose(gv, ov, rtol=2e-6, atol=1e-6)
+        assert np.array_equal(gn[..., 0] == -2, on[..., 0] == -2)
+    assert (od > 0).mean() > 0.5
