@@ -47,13 +47,15 @@ def check(g, p, k, mu, exact, vertex_normal):
         assert np.array_equal(p.render_volume(g["poses"][0], k, mu, 0.75 * mu, True), g["render_view"])
     else:
         assert np.array_equal(data["y"], g["block_y"])            # timestamps are exact
-        np.testing.assert_allclose(data["x"], g["block_x"], rtol=REL_TOL, atol=1e-5)
-        np.testing.assert_allclose(values["x"], g["node_x"], rtol=REL_TOL, atol=1e-5)
+        # tolerances: what is measured on the device plus a small factor (tests/test_gpu_parity.py, OFU_*): occupancies 1 ulp
+        # apart where glibc's log2f is not correctly rounded, everything else identical
+        np.testing.assert_allclose(data["x"], g["block_x"], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(values["x"], g["node_x"], rtol=2e-6, atol=1e-7)
         ghit, hit = g["normal"][..., 0] != -2, n[..., 0] != -2
-        assert np.count_nonzero(ghit != hit) <= 0.002 * hit.size   # a hit can flip where occupancy crosses 0 within tolerance
+        assert np.count_nonzero(ghit != hit) <= 2e-5 * hit.size + 1   # a hit can flip where an occupancy 1 ulp off crosses 0 (observed: none)
         both = ghit & hit
-        np.testing.assert_allclose(v[both], g["vertex"][both], rtol=REL_TOL, atol=2e-4)
-        np.testing.assert_allclose(n[both], g["normal"][both], rtol=0, atol=2e-3)
+        np.testing.assert_allclose(v[both], g["vertex"][both], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(n[both], g["normal"][both], rtol=0, atol=1e-6)
     assert np.array_equal(p.render_depth(), g["render_depth"])
 
 

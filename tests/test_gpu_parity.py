@@ -176,27 +176,37 @@ def test_sdf_2048_deep_tree_properties_and_sampled_parity():
 
 
 # ---- OFusion ---------------------------------------------------------------------------------
+# What the OFusion path is held to.  north_star's bar is 1e-4 relative; MEASURED on the B200 (scripts/ofusion_deviation.py, round 2:
+# four scenarios, 160x120 .. 640x480 into 256^3 .. 1024^3) the only differences are occupancies 1 ulp apart (<= 4.8e-7 relative,
+# where glibc's log2f is not the correctly rounded value the device computes -- 0 to 0.13 % of the voxels), no hit flips, no
+# differing vertex bit and at most one normal component 1 ulp off.  The assertions sit a small factor above that.
+OFU_X_RTOL = 2e-6          # occupancy (log-odds), relative: 4 ulp
+OFU_FLIPS = 2e-5           # fraction of pixels whose hit / miss may differ: a handful per 640x480 image (observed: none)
+OFU_VERTEX_ATOL = 2e-6     # metres (observed: bit-identical)
+OFU_NORMAL_ATOL = 1e-6     # (observed: <= 1.5e-8)
+
+
 def assert_ofusion_parity(g, o, pose, k, mu):
     gk, gc, ga, gd = g.blocks_sorted()
     ok, oc, oa, od = o.blocks_sorted()
     assert np.array_equal(gk, ok), (len(gk), len(ok), len(np.setdiff1d(gk, ok)), len(np.setdiff1d(ok, gk)))   # allocation set bit-exact
     assert np.array_equal(gc, oc) and np.array_equal(ga, oa)
     assert np.array_equal(gd["y"], od["y"])                                 # timestamps exact
-    np.testing.assert_allclose(gd["x"], od["x"], rtol=REL_TOL, atol=1e-5)
+    np.testing.assert_allclose(gd["x"], od["x"], rtol=OFU_X_RTOL, atol=1e-7)
     gcodes, gs, gm, gvv = g.nodes_sorted()
     ocodes, os_, om, ovv = o.nodes_sorted()
     assert np.array_equal(gcodes, ocodes) and np.array_equal(gs, os_) and np.array_equal(gm, om)
-    np.testing.assert_allclose(gvv["x"], ovv["x"], rtol=REL_TOL, atol=1e-5)
+    np.testing.assert_allclose(gvv["x"], ovv["x"], rtol=OFU_X_RTOL, atol=1e-7)
     assert np.array_equal(gvv["y"], ovv["y"])
     o.raycast(pose, k, mu); g.raycast(pose, k, mu)
     gv, gn = g.vertex_normal()
     ov, on = o.vertex(), o.normal()
     ghit, ohit = gn[..., 0] != -2, on[..., 0] != -2
     assert ghit.sum() > 0.5 * ghit.size
-    assert np.count_nonzero(ghit != ohit) <= 0.002 * ghit.size
+    assert np.count_nonzero(ghit != ohit) <= OFU_FLIPS * ghit.size
     both = ghit & ohit
-    np.testing.assert_allclose(gv[both], ov[both], rtol=REL_TOL, atol=2e-4)
-    np.testing.assert_allclose(gn[both], on[both], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(gv[both], ov[both], rtol=0, atol=OFU_VERTEX_ATOL)
+    np.testing.assert_allclose(gn[both], on[both], rtol=0, atol=OFU_NORMAL_ATOL)
     bit_equal = np.count_nonzero(gd["x"].view(np.uint32) != od["x"].view(np.uint32))
     return bit_equal / gd["x"].size
 
@@ -209,7 +219,7 @@ def test_ofusion_1024_room_sequence():
     g, o = make_pair(OFUSION, 1024, dim, W, H)
     pose = run_sequence(g, o, synth.box_room, dim, W, H, k, mu, range(0, 20, 4), n_frames=300, dropout=0.01)
     frac = assert_ofusion_parity(g, o, pose, k, mu)
-    assert frac < 1e-3          # bit-identical except where glibc's log2f is not the correctly rounded value (1 ulp; observed: none)
+    assert frac < 2e-3          # bit-identical except where glibc's log2f is not the correctly rounded value (1 ulp; observed: none here, <= 0.13 % elsewhere)
     assert np.array_equal(g.render_volume(pose, k, mu, 0.75 * mu, False)[..., 3], o.render_volume(pose, k, mu, 0.75 * mu, False)[..., 3])
 
 

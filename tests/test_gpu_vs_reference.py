@@ -6,7 +6,7 @@ sizes BASELINE.json quotes: 640x480 frames into the 512^3 TSDF map (configs[1]) 
 side and through the reference's DenseSLAMSystem::{preprocessing, integration, raycasting} + renderVolumeKernel on the other
 (single-threaded, in a fresh process: tests/_ref_frames_worker.py), plus one full-size frame of configs[2] and configs[3]
 against the oracle.  Bars as everywhere: SDF bit-exact; OFusion occupancies within 1e-4 relative (log2f: libm vs device),
-timestamps and the allocation set exact."""
+timestamps and the allocation set exact, everything else to the measured-level tolerances of tests/test_gpu_parity.py (OFU_*)."""
 import os
 import subprocess
 import sys
@@ -17,7 +17,7 @@ import pytest
 import oracle_lib
 from oracle_lib import OFUSION, SDF
 from parity_utils import compare_blocks, compare_images
-from test_gpu_parity import K640, REL_TOL, assert_ofusion_parity, make_pair, run_sequence
+from test_gpu_parity import K640, OFU_FLIPS, OFU_NORMAL_ATOL, OFU_VERTEX_ATOL, OFU_X_RTOL, assert_ofusion_parity, make_pair, run_sequence
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -76,15 +76,16 @@ def test_ofusion_512_frames_against_the_reference_build(tmp_path):
     keys, coords, active, data = g.blocks_sorted()
     assert len(keys) > 3000 and np.array_equal(keys, ref["keys"]) and np.array_equal(coords, ref["coords"]) and np.array_equal(active, ref["active"])
     assert np.array_equal(data["y"], ref["data"]["y"])
-    np.testing.assert_allclose(data["x"], ref["data"]["x"], rtol=REL_TOL, atol=1e-5)
+    np.testing.assert_allclose(data["x"], ref["data"]["x"], rtol=OFU_X_RTOL, atol=1e-7)
     codes, side, mask, values = g.nodes_sorted()
     assert np.array_equal(codes, ref["codes"]) and np.array_equal(side, ref["side"]) and np.array_equal(values["y"], ref["values"]["y"])
-    np.testing.assert_allclose(values["x"], ref["values"]["x"], rtol=REL_TOL, atol=1e-5)
+    np.testing.assert_allclose(values["x"], ref["values"]["x"], rtol=OFU_X_RTOL, atol=1e-7)
     gv, gn = g.vertex_normal()
     ghit, rhit = gn[..., 0] != -2, ref["normal"][..., 0] != -2
-    assert ghit.sum() > 0.5 * ghit.size and np.count_nonzero(ghit != rhit) <= 1e-3 * ghit.size
+    assert ghit.sum() > 0.5 * ghit.size and np.count_nonzero(ghit != rhit) <= OFU_FLIPS * ghit.size
     both = ghit & rhit
-    np.testing.assert_allclose(gv[both], ref["vertex"][both], rtol=REL_TOL, atol=2e-4)
+    np.testing.assert_allclose(gv[both], ref["vertex"][both], rtol=0, atol=OFU_VERTEX_ATOL)
+    np.testing.assert_allclose(gn[both], ref["normal"][both], rtol=0, atol=OFU_NORMAL_ATOL)
 
 
 def test_ofusion_1024_one_full_size_frame_against_the_oracle():

@@ -109,7 +109,7 @@ def test_shim_frame_loop_matches_oracle(tmp_path, field, mu):
         assert np.array_equal(norm.view(np.uint32), o.normal().view(np.uint32))
         assert np.array_equal(vol.reshape(H, W, 4), o.render_volume(poses[-1], k, mu, 0.75 * mu, False))
     else:
-        np.testing.assert_allclose(gd["x"], data["x"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(gd["x"], data["x"], rtol=2e-6, atol=1e-7)      # (1 ulp where glibc log2f is not correctly rounded: tests/test_gpu_parity.py OFU_*)
         assert np.array_equal(gd["y"], data["y"])
     assert np.array_equal(dep.reshape(H, W, 4), o.render_depth())
     assert np.all(trk.reshape(H, W, 4)[..., :3] == np.array([255, 128, 128], np.uint8))     # result 0 -> default colour (rendering.cpp:203-208)
@@ -154,7 +154,7 @@ def test_map_file_exchange_with_the_reference(tmp_path, field, mu):
         assert blocks["voxels"].tobytes() == data.tobytes() and nodes["value"].tobytes() == values.tobytes()
         tmf.same_octree(ref, back, reloaded_by_reference=True)
     else:
-        np.testing.assert_allclose(blocks["voxels"]["x"], data["x"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(blocks["voxels"]["x"], data["x"], rtol=2e-6, atol=1e-7)
         assert np.array_equal(blocks["voxels"]["y"], data["y"])
         kb, cb, _, _ = back.blocks_sorted(with_data=False)
         assert np.array_equal(kb, keys) and np.array_equal(cb, coords) and np.array_equal(back.nodes_sorted()[0], codes)
@@ -171,6 +171,6 @@ def test_map_file_exchange_with_the_reference(tmp_path, field, mu):
         assert np.array_equal(lvert.view(np.uint32), rv.view(np.uint32)) and np.array_equal(lnorm.view(np.uint32), rn.view(np.uint32))
     else:
         hit_g, hit_r = lnorm[..., 0] != -2.0, rn[..., 0] != -2.0
-        assert (hit_g != hit_r).mean() < 2e-3
+        assert (hit_g != hit_r).mean() <= 2e-5
         both = hit_g & hit_r
-        np.testing.assert_allclose(lvert[both], rv[both], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(lvert[both], rv[both], rtol=0, atol=2e-6)
