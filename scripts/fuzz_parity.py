@@ -4,6 +4,9 @@ every scenario the block set, voxel and node values, vertex / normal maps and bo
 for the SDF field, to the test suite's tolerances for OFusion.
   python scripts/fuzz_parity.py [n_scenarios] [first_seed]
   python scripts/fuzz_parity.py --ref <size> [n_scenarios] [first_seed]
+  python scripts/fuzz_parity.py --ref-device <size> [n_scenarios] [first_seed]
+With --ref-device the PRODUCT is compared directly with the reference's own code over the --ref scenario domain (the reference's
+defined domain, see below): one hop instead of product == oracle == reference.
 With --ref the same scenarios compare the ORACLE with the reference's own code (oracle/_ref, built where /root/reference exists)
 instead of the product with the oracle -- every array bit for bit, both fields, overflowing allocation lists included (single
 thread: the truncation is then deterministic).  One volume size per process: the reference keeps a `static const float epsilon`
@@ -134,7 +137,7 @@ def random_depth(rng, W, H, dim):
     return np.ascontiguousarray(out)
 
 
-def scenario(seed, ref_size=0):
+def scenario(seed, ref_size=0, device_vs_ref=False):
     rng = np.random.default_rng(seed)
     field = int(rng.integers(2))
     size = int(rng.choice([16, 32, 64, 128, 256]))
@@ -147,7 +150,8 @@ def scenario(seed, ref_size=0):
     mu = float(rng.choice([0.1, 0.05, 0.02]) if field == SDF else rng.choice([0.008, 0.02]))
     if field == SDF and 2 * mu / (dim / size) > 90:
         mu = 40 * dim / size                              # keeps the band below the per-ray block list (100 samples)
-    g, o = (RefAsMap if ref_size else Map)(field, size, dim, W, H), Oracle(field, size, dim, W, H)
+    g, o = (RefAsMap if ref_size and not device_vs_ref else Map)(field, size, dim, W, H), Oracle(field, size, dim, W, H)
+    ref = RefAsMap(field, size, dim, W, H) if device_vs_ref else None      # --ref-device: product vs reference; the oracle only gates the domain
     o.set_counting(True)
     reserved = (size // 8) * W * H             # DenseSLAMSystem.cpp:212-215
     n_frames = int(rng.integers(1, 5))
@@ -162,12 +166,17 @@ def scenario(seed, ref_size=0):
         o.preprocess(d); o.integrate(pose, k, mu, fr)
         if ref_size and o.counters()["n_keys_raw"] == 0:
             return None        # allocate(keys, 0): the reference processes one stale key of an earlier frame (unique.hpp:51-60), undefined
-        if o.counters()["n_keys_raw"] >= reserved and not ref_size:
+        if o.counters()["n_keys_raw"] >= reserved and (not ref_size or device_vs_ref):
             # The reference stops recording requests when its reserved list is full (alloc_impl.hpp:103-106); which requests
             # are lost depends on the OpenMP interleaving, so there is no reference answer.  (The library has no such list.)
             return None
         g.preprocess(d); g.integrate(pose, k, mu, fr)
+        if ref is not None:
+            ref.preprocess(d); ref.integrate(pose, k, mu, fr)
     problems = []
+    if ref is not None:
+        o = ref
+    exact = field == SDF or (ref_size and not device_vs_ref)               # OFusion on the device: log2f is 1 ulp off glibc's on some arguments
     cb = compare_blocks(g, o)
     if not cb["keys_equal"]:
         return [f"block sets differ {cb}"]
@@ -176,7 +185,7 @@ def scenario(seed, ref_size=0):
     cn = compare_nodes(g, o)
     if not (cn["codes_equal"] and cn.get("side_equal") and cn.get("mask_equal")):
         problems.append(f"nodes {cn}")
-    if field == SDF or ref_size:
+    if exact:
         if cb["x_bit_mismatch"] or cb["y_mismatch"] or cn.get("x_bit_mismatch") or cn.get("y_mismatch"):
             problems.append(f"SDF values {cb} {cn}")
     else:
@@ -196,7 +205,7 @@ def scenario(seed, ref_size=0):
         ov_, rv_ = o.vertex() * (size / dim), gv * (size / dim)
         for v_, n_ in ((ov_, o.normal()), (rv_, gn)):
             at_face |= (n_[..., 0] != -2.0) & ((v_ < 2.0) | (v_ > size - 3.0)).any(axis=-1)
-    if field == SDF or ref_size:
+    if exact:
         differs = (gv.view(np.uint32) != o.vertex().view(np.uint32)).any(axis=-1) | (gn.view(np.uint32) != o.normal().view(np.uint32)).any(axis=-1)
         if (differs & ~at_face).any():
             problems.append(f"raycast {ci}")
@@ -234,8 +243,9 @@ def scenario(seed, ref_size=0):
 
 if __name__ == "__main__":
     argv = sys.argv[1:]
-    ref_size = 0
-    if argv and argv[0] == "--ref":
+    ref_size, device_vs_ref = 0, False
+    if argv and argv[0] in ("--ref", "--ref-device"):
+        device_vs_ref = argv[0] == "--ref-device"
         ref_size, argv = int(argv[1]), argv[2:]
         if not oracle_lib.have_reference_build():
             sys.exit("oracle/_ref is not built (it needs /root/reference: `make -C oracle ref`)")
@@ -245,7 +255,7 @@ if __name__ == "__main__":
     bad = skipped = 0
     for s in range(first, first + n):
         try:
-            p = scenario(s, ref_size)
+            p = scenario(s, ref_size, device_vs_ref)
         except Exception as e:                       # an error return of the library is a finding too
             p = [f"{type(e).__name__}: {e}"]
         if p is None:

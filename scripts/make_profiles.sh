@@ -15,7 +15,7 @@ capture() {  # workload kernels-per-frame frame regex
   ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s $((PER * FRAME)) -c $PER \
       -o gpurun_out/${R}_full_${WL} python scripts/profile_frames.py $WL $((FRAME + 2)) > gpurun_out/${R}_full_${WL}.log 2>&1
 }
-capture planar_sweep_sdf512 4 160 "k_alloc_sdf|k_integrate_sdf|k_raycast|k_render_shade"
-capture box_room_sdf2048 4 20 "k_alloc_sdf|k_integrate_sdf|k_raycast|k_render_shade"
+capture planar_sweep_sdf512 5 160 "k_alloc_sdf|k_filter_blocks|k_integrate_sdf|k_raycast|k_render_shade"
+capture box_room_sdf2048 5 20 "k_alloc_sdf|k_filter_blocks|k_integrate_sdf|k_raycast|k_render_shade"
 capture box_room_ofusion1024 5 20 "k_alloc_ofusion|k_alloc_first|k_integrate_ofusion|k_raycast|k_render_shade"
 ls -la gpurun_out

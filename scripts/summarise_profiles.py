@@ -17,7 +17,7 @@ OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 STAGE = {"k_mm2meters": "preprocess", "k_alloc_sdf": "alloc", "k_alloc_ofusion": "alloc", "k_alloc_first_key_chain": "alloc",
-         "k_integrate_sdf": "fuse", "k_integrate_ofusion": "fuse", "k_raycast": "raycast",
+         "k_filter_blocks": "alloc", "k_integrate_sdf": "fuse", "k_integrate_ofusion": "fuse", "k_raycast": "raycast",
          "k_render_shade": "render", "k_render_volume": "render"}
 WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
@@ -81,7 +81,7 @@ def full(workload, traffic):
         t[stage] += sum(v) / len(v)                 # mean per launch, summed over the kernels of the stage
     traffic[workload] = {k: int(v) for k, v in t.items()}
     with open(os.path.join(OUT, f"{R}_sass_{workload}.txt"), "w") as f:
-        for kern in ("k_raycast", "k_alloc_sdf", "k_alloc_ofusion", "k_integrate_sdf", "k_integrate_ofusion"):
+        for kern in ("k_raycast", "k_alloc_sdf", "k_alloc_ofusion", "k_filter_blocks", "k_integrate_sdf", "k_integrate_ofusion"):
             src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kern}"], capture_output=True, text=True).stdout
             if "Address" not in src:
                 continue

@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "config.h"
@@ -49,6 +50,20 @@ struct MapSnapshot {                                   // what Octree::save writ
   // reference writes pool order, which is arbitrary there too).
   bool save(const std::string& filename) const;
   bool load(const std::string& filename);
+
+  // A host mirror of the read accessors a caller of getMap() uses on the reference's se::Octree, over the records held here:
+  //   fetch     Octree::fetch (octree.hpp:440-458): index of the block containing voxel (x, y, z) in block_keys, -1 if none
+  //   get_fine  Octree::get_fine (:356-377): the voxel, initValue() where nothing is allocated
+  //   interp    Octree::interp with select = .x (:541-563, interpolation/interp_gather.hpp:105-237): trilinear, voxel units
+  // (voxels outside [0, size) read initValue(): the reference indexes out of bounds there).  Records need not be sorted.
+  int fetch(int x, int y, int z) const;
+  FieldType get_fine(int x, int y, int z) const;
+  float interp(float x, float y, float z) const;
+  static FieldType initValue();
+
+ private:
+  mutable std::vector<std::pair<uint64_t, int>> index_;      // (key, position in block_keys), sorted; built on the first query
+  void build_index() const;
 };
 }  // namespace se
 

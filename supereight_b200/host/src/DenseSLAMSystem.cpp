@@ -11,6 +11,8 @@
 
 #include "se_b200.h"
 #include <iostream>
+#include <cmath>
+#include <algorithm>
 
 namespace {
 constexpr int kFieldType = std::is_same<FieldType, SDF>::value ? SE_B200_SDF : SE_B200_OFUSION;
@@ -208,6 +210,59 @@ bool se::MapSnapshot::load(const std::string& filename) {
     is.read((char*)&block_voxels[512 * i], sizeof(FieldType) * 512);
   }
   return (bool)is;
+}
+
+// ---- host mirror of Octree::fetch / get_fine / interp over a snapshot -------------------------------------------------
+namespace {
+uint64_t spread3(uint64_t v) {                       // morton_utils.hpp:37-49: one coordinate's bits to every third position
+  uint64_t x = v & 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+int log2i(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+}  // namespace
+
+FieldType se::MapSnapshot::initValue() {              // volume_traits.hpp:41-72
+  FieldType v{};
+  v.x = std::is_same<FieldType, SDF>::value ? 1.f : 0.f;
+  v.y = 0;
+  return v;
+}
+
+void se::MapSnapshot::build_index() const {
+  index_.resize(block_keys.size());
+  for (size_t i = 0; i < block_keys.size(); ++i) index_[i] = std::make_pair(block_keys[i], (int)i);
+  std::sort(index_.begin(), index_.end());
+}
+
+int se::MapSnapshot::fetch(int x, int y, int z) const {
+  if (x < 0 || y < 0 || z < 0 || x >= size || y >= size || z >= size) return -1;
+  if (index_.size() != block_keys.size()) build_index();
+  const int max_level = log2i(size), level = max_level - 3;              // blocks live at the leaves level (octree.hpp:205-212)
+  const uint64_t morton = spread3((uint64_t)(x & ~7)) | (spread3((uint64_t)(y & ~7)) << 1) | (spread3((uint64_t)(z & ~7)) << 2);
+  const uint64_t key = morton | (uint64_t)level;                         // (the block's low corner has no bits below the level's mask)
+  auto it = std::lower_bound(index_.begin(), index_.end(), std::make_pair(key, -1));
+  return (it != index_.end() && it->first == key) ? it->second : -1;
+}
+
+FieldType se::MapSnapshot::get_fine(int x, int y, int z) const {
+  const int b = fetch(x, y, z);
+  if (b < 0) return initValue();
+  return block_voxels[(size_t)b * 512 + (x & 7) + 8 * (y & 7) + 64 * (z & 7)];
+}
+
+float se::MapSnapshot::interp(float px, float py, float pz) const {
+  const float flx = std::floor(px), fly = std::floor(py), flz = std::floor(pz);
+  const float fx = px - flx, fy = py - fly, fz = pz - flz;
+  const int bx = std::max((int)flx, 0), by = std::max((int)fly, 0), bz = std::max((int)flz, 0);
+  float p[8];
+  for (int i = 0; i < 8; ++i) p[i] = get_fine(bx + (i & 1), by + ((i >> 1) & 1), bz + ((i >> 2) & 1)).x;    // empty().x == initValue().x
+  return (((p[0] * (1 - fx) + p[1] * fx) * (1 - fy) + (p[2] * (1 - fx) + p[3] * fx) * fy) * (1 - fz)
+        + ((p[4] * (1 - fx) + p[5] * fx) * (1 - fy) + (p[6] * (1 - fx) + p[7] * fx) * fy) * fz);
 }
 
 void DenseSLAMSystem::getVertexNormal(std::vector<float>& vertex, std::vector<float>& normal) {

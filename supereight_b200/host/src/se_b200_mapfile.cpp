@@ -3,10 +3,13 @@
 // shim's se::MapSnapshot, the same code DenseSLAMSystem::getMap() / setMap() and se_b200_benchmark -b use.
 //   copy <in> <out>    load, then save: a file written by the reference comes out byte for byte (records keep their order)
 //   sort <in> <out>    load, sort nodes and blocks by key (the order getMap() exports), save
-//   info <in>          size, dim, node and block counts, key range
+//   info <in>          size, dim, node and block counts
+//   query <in> <points> <out>   points: lines "x y z" (floats, voxel units); out: "get_fine.x get_fine.y interp" per line, with
+//                      get_fine at the truncated coordinates -- se::MapSnapshot's host mirror of Octree::get_fine / interp
 // Needs no GPU: nothing here touches the device.
 #include <algorithm>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <numeric>
 #include <string>
@@ -31,8 +34,8 @@ static void sort_by_key(se::MapSnapshot& s) {
 
 int main(int argc, char** argv) {
   const std::string cmd = argc > 1 ? argv[1] : "";
-  if (!((cmd == "info" && argc == 3) || ((cmd == "copy" || cmd == "sort") && argc == 4))) {
-    std::cerr << "usage: " << argv[0] << " copy|sort <in> <out>  |  info <in>" << std::endl;
+  if (!((cmd == "info" && argc == 3) || ((cmd == "copy" || cmd == "sort") && argc == 4) || (cmd == "query" && argc == 5))) {
+    std::cerr << "usage: " << argv[0] << " copy|sort <in> <out>  |  info <in>  |  query <in> <points> <out>" << std::endl;
     return 2;
   }
   se::MapSnapshot s;
@@ -40,6 +43,17 @@ int main(int argc, char** argv) {
   if (cmd == "info") {
     std::cout << "size " << s.size << " dim " << s.dim << " nodes " << s.node_codes.size() << " blocks " << s.block_keys.size() << std::endl;
     return 0;
+  }
+  if (cmd == "query") {
+    std::ifstream pts(argv[3]);
+    std::ofstream out(argv[4]);
+    out.precision(17);
+    float x, y, z;
+    while (pts >> x >> y >> z) {
+      const FieldType v = s.get_fine((int)x, (int)y, (int)z);
+      out << v.x << " " << (double)v.y << " " << s.interp(x, y, z) << "\n";
+    }
+    return out ? 0 : 1;
   }
   if (cmd == "sort") sort_by_key(s);
   if (!s.save(argv[3])) { std::cerr << "cannot write " << argv[3] << std::endl; return 1; }

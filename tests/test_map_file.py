@@ -132,3 +132,30 @@ def test_point_queries_on_a_reloaded_map_match(tmp_path, field):
         assert o.get_fine(x, y, z) == back.get_fine(x, y, z)
     assert not back.fetch(0, 0, 0) or o.fetch(0, 0, 0)
     back.close()
+
+
+@pytest.mark.parametrize("field", ["sdf", "ofusion"])
+def test_snapshot_host_mirror_of_get_and_interp(tmp_path, field):
+    """se::MapSnapshot::get_fine / interp -- what a caller of getMap() uses on the reference's se::Octree -- against the
+    reference's own Octree::get_fine / interp on the map the file came from: bit for bit."""
+    o, fid = reference_map(field)
+    a = str(tmp_path / "reference.bin")
+    o.save_map(a)
+    _, coords, _, _ = o.blocks_sorted(with_data=False)
+    rng = np.random.default_rng(11)
+    pts = []
+    for bc in coords[rng.choice(len(coords), min(150, len(coords)), replace=False)]:
+        pts.append(bc + rng.uniform(0.0, 8.0, 3))                      # inside allocated blocks, block borders included
+    pts += list(rng.uniform(2, o.size - 3, (100, 3)))                  # anywhere (mostly unallocated)
+    pts = np.clip(np.array(pts, np.float32), 1.0, o.size - 3.0)
+    pfile, ofile = str(tmp_path / "points.txt"), str(tmp_path / "out.txt")
+    np.savetxt(pfile, pts, fmt="%.9g")
+    subprocess.run([tool(field), "query", a, pfile, ofile], check=True)
+    got = np.loadtxt(ofile).reshape(len(pts), 3)
+    hits = 0
+    for q, g in zip(np.loadtxt(pfile, dtype=np.float32).reshape(-1, 3), got):
+        vx, vy = o.get_fine(int(q[0]), int(q[1]), int(q[2]))
+        assert np.float32(g[0]) == np.float32(vx) and float(g[1]) == float(vy), (q, g, vx, vy)
+        assert np.float32(g[2]) == np.float32(o.interp(float(q[0]), float(q[1]), float(q[2]))), (q, g)
+        hits += vy != 0 or np.float32(vx) != np.float32(1.0 if field == "sdf" else 0.0)
+    assert hits > (50 if field == "sdf" else 5)

@@ -104,3 +104,20 @@ def test_randomised_parity_scenarios_on_the_device():
                        capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " 0 with differences" in r.stdout, r.stdout[-1000:]
+
+
+@pytest.mark.parametrize("size", [64, 256])
+def test_randomised_scenarios_product_against_the_reference_build(size):
+    """scripts/fuzz_parity.py --ref-device: the product DIRECTLY against the reference's own code (oracle/_ref) over the
+    reference's defined domain -- cameras and surfaces inside the volume -- one volume size per process."""
+    import os
+    import subprocess
+    import sys
+    import oracle_lib
+    if not oracle_lib.have_reference_build():
+        pytest.skip("oracle/_ref (the reference build) is absent")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "--ref-device", str(size), "40", "7000"], cwd=root,
+                       capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " 0 with differences" in r.stdout, r.stdout[-1000:]
