@@ -78,9 +78,12 @@ int se_b200_sync(se_b200_map* map);
  * se_b200_device_image(0) -- triggers a conversion kernel first); results are those of the eager kernel, bit for bit.
  * Buffer lifetime.  _host with PAGE-LOCKED memory: the copy is asynchronous -- do not modify depth_mm until a
  * synchronising call (se_b200_sync, any call that returns data to host memory) has returned; pageable memory is staged
- * before the call returns.  _device: depth_mm_dev is READ LATER, in stream order, by that next consumer -- keep it valid
+ * before the call returns.  _device: depth_mm_dev is READ LATER by that next consumer -- keep it valid
  * and unchanged until the work of the se_b200_integrate (or other consumer) that follows has been enqueued AND anything
- * you then do to the buffer is ordered after the map's stream.
+ * you then do to the buffer is ordered after the map's stream; and it must HOLD the frame when the call is made (written and
+ * device-visible -- e.g. produced by work the caller has synchronised, or that precedes the previous frame's calls in the
+ * map's stream): for SDF maps the allocation kernel that reads it runs on a second, internal stream, ordered behind the
+ * previous frame's integrate kernel but not behind its raycast (frames overlap; results are those of the serial order).
  * se_b200_register_host_buffer page-locks (cudaHostRegister) a caller-owned buffer -- the reference application malloc()s its
  * depth and RGBA buffers (se_apps/src/benchmark.cpp:90-97), which makes every transfer a staged, synchronous copy; registering
  * them once makes the _host calls above and below asynchronous / zero-copy.  Unregister before freeing the memory. */
