@@ -414,6 +414,10 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   ip.voxelSize = voxelsize; ip.mu = mu;
   ip.timestamp = (1.f / 30.f) * (float)frame;                            // DenseSLAMSystem.cpp:243
   ip.W = m->W; ip.H = m->H;
+  ip.rmu = 1.f / mu; ip.wlim = (float)m->W - 1.5f; ip.hlim = (float)m->H - 1.5f; ip.wf = (float)m->W; ip.no_sample = kPixMagicBits + (unsigned)(m->W * m->H);
+  ip.one2 = make_float2(1.f, 1.f); ip.mone2 = make_float2(-1.f, -1.f);
+  ip.tz2 = make_float2(Tcw.m[2], Tcw.m[6]); ip.tt2 = make_float2(Tcw.m[3], Tcw.m[7]);
+  ip.nkd2 = make_float2(-K.m[0], -K.m[5]); ip.nkz2 = make_float2(-K.m[2], -K.m[6]);
   // persistent grid-stride kernels: exactly as many CTAs as are resident at once (one wave), trip
   // counts read from device counters
   if (m->grid_integrate == 0) {
@@ -429,7 +433,8 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   }
   // the check-free division/sqrt sequences need every operand in the normal float range: guaranteed when
   // the matrices, the voxel size and mu are 0 or within [2^-20, 2^20]; anything else takes the plain IEEE kernel
-  bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f;
+  // (... and its pixel index is formed in fp32, exact for images of fewer than 2^22 pixels: sdf_voxel_pair)
+  bool fast = !getenv("SE_B200_IEEE_DIV") && normal_range(voxelsize) && normal_range(mu) && mu > 0.f && (long long)m->W * m->H < (1ll << 22);
   for (int i = 0; i < 12 && fast; ++i) fast = normal_range(Tcw.m[i]) && normal_range(K.m[i]);
   if (FieldTraits<V>::is_sdf) {
     if (fast) launch_pdl(k_integrate_sdf<true>, m->grid_integrate, kIntegrateWarps * 32, kIntegrateSmem, m->stream, m->view<SdfVoxel>(), m->d_depth, ip, fp, m->d_active_list, miss, parity, m->d_status, prefiltered);
@@ -703,13 +708,14 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
   std::memset(m->h_status, 0, 4 * sizeof(int));
   CREATE_TRY(cudaHostGetDevicePointer((void**)&m->d_status, m->h_status, 0));
   const size_t npx = (size_t)W * H;
-  CREATE_TRY(cudaMalloc(&m->d_depth, npx * sizeof(float)));
+  // (one float more than the image, always 0: "no depth sample" for the voxels the check-free SDF integrate finds outside the image -- sdf_voxel_pair)
+  CREATE_TRY(cudaMalloc(&m->d_depth, (npx + 1) * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_vertex, npx * 3 * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_normal, npx * 3 * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_rgba, npx * sizeof(uchar4)));
   CREATE_TRY(cudaMalloc(&m->d_active_list, (size_t)m->max_blocks * sizeof(int)));
   CREATE_TRY(cudaMemsetAsync(m->d_active_list, 0xFF, (size_t)m->max_blocks * sizeof(int), m->stream));      // kEmpty: the list is streamed (ActiveList)
-  CREATE_TRY(cudaMemsetAsync(m->d_depth, 0, npx * sizeof(float), m->stream));
+  CREATE_TRY(cudaMemsetAsync(m->d_depth, 0, (npx + 1) * sizeof(float), m->stream));
   CREATE_TRY(cudaMemsetAsync(m->d_vertex, 0, npx * 3 * sizeof(float), m->stream));
   CREATE_TRY(cudaMemsetAsync(m->d_normal, 0, npx * 3 * sizeof(float), m->stream));
   float lut[1000];      // function scope: it outlives the stream-ordered copy below (create_pools ends with a synchronisation)

@@ -43,6 +43,8 @@ __device__ __forceinline__ unsigned long long pk(float2 a) { return (unsigned lo
 __device__ __forceinline__ float2 upk(unsigned long long v) { return make_float2(__uint_as_float((unsigned)v), __uint_as_float((unsigned)(v >> 32))); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d); }
+// (round toward zero: x + 2^23 then has trunc(x) in its low mantissa bits, 0 <= x < 2^22)
+__device__ __forceinline__ float2 add2_rz(float2 a, float2 b) { unsigned long long d; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b))); return upk(d); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c))); return upk(d); }
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): global -> shared, completion counted in bytes ------
@@ -63,6 +65,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   }
+}
+// 16 bytes of shared memory by their 32-bit shared-window address (kept in one register: the generic-pointer form had its
+// address re-derived from the CTA's window base in every slice of the integrate loop)
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 // makes the mbarrier initialisation visible to the async proxy before the first bulk copy
 __device__ __forceinline__ void mbar_init_fence() {

@@ -25,10 +25,21 @@ __device__ __forceinline__ unsigned long long pk(float2 a) { return (unsigned lo
 __device__ __forceinline__ float2 upk(unsigned long long v) { return make_float2(__uint_as_float((unsigned)v), __uint_as_float((unsigned)(v >> 32))); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float add_rz_emu(float a, float b) {
+  const int old = std::fegetround();
+  std::fesetround(FE_TOWARDZERO);
+  volatile float va = a, vb = b;
+  volatile float r = va + vb;
+  std::fesetround(old);
+  return r;
+}
+__device__ __forceinline__ float2 add2_rz(float2 a, float2 b) { return make_float2(add_rz_emu(a.x, b.x), add_rz_emu(a.y, b.y)); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
 
 // mbarrier word: number of completed phases (one producer, transaction-count completion only)
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)(size_t)p; }
+// shared-window address: the offset from the CTA's dynamic shared memory (the only thing the kernels address this way)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)((const unsigned char*)p - simt::dynamic_smem()); }
+__device__ __forceinline__ float4 lds128(unsigned addr) { return *reinterpret_cast<const float4*>((simt::dynamic_smem() + addr)); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int) { *bar = 0; }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
