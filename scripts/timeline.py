@@ -1,0 +1,49 @@
+"""Phase time stamps of the integrate kernel, per CTA (SE_TIMELINE build of the library: supereight_b200/variants/libse_b200_timeline.so,
+`nvcc ... -DSE_TIMELINE`).  Usage: SE_B200_LIB=<that build> python scripts/timeline.py [workload] [frames]"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import bench
+from supereight_b200 import Map, capi
+
+name = sys.argv[1] if len(sys.argv) > 1 else "box_room_sdf2048"
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 22
+cfg = bench.WORKLOADS[name]
+depth, poses, k = bench.make_frames(cfg, frames, 0)
+m = Map(cfg["field"], cfg["size"], cfg["dim"], cfg["W"], cfg["H"], max_blocks=cfg.get("max_blocks", 0))
+lib = capi.load_library()
+lib.se_b200_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+mu = cfg["mu"]
+for f in range(frames):
+    m.preprocess(depth[f])
+    m.integrate(poses[f], k, mu, f)
+    if f == frames - 1:
+        n = 592
+        buf = np.zeros(8 * n, np.uint64)
+        assert lib.se_b200_debug_timeline(m.h, buf.ctypes.data, 8 * n) == 0
+        t = buf.reshape(n, 8)[:, :5].astype(np.int64)
+        t0 = t[:, 0].min()
+        t = (t - t0) / 1000.0
+        names = ["start", "list produced", "blocks done (warp 0)", "list complete", "nodes done"]
+        for i, nm in enumerate(names):
+            print(f"{nm:24s} min {t[:, i].min():8.1f}  median {np.median(t[:, i]):8.1f}  max {t[:, i].max():8.1f} us")
+    m.raycast(poses[f], k, mu)
+    if f == frames - 1:
+        n = 2400
+        buf = np.zeros(8 * n, np.uint64)
+        assert lib.se_b200_debug_timeline(m.h, buf.ctypes.data, 8 * n) == 0
+        t = buf.reshape(n, 8)[:, 5:7].astype(np.int64)
+        t = (t - t[:, 0].min()) / 1000.0
+        dur = t[:, 1] - t[:, 0]
+        end = t[:, 1].max()
+        print(f"raycast: {n} CTAs, kernel {end:.1f} us; CTA duration (thread 0) min {dur.min():.1f} median {np.median(dur):.1f} p90 {np.percentile(dur, 90):.1f} max {dur.max():.1f} us")
+        print("  CTA starts: p50 %.1f p90 %.1f max %.1f us" % (np.median(t[:, 0]), np.percentile(t[:, 0], 90), t[:, 0].max()))
+        for back in (2, 4, 6, 8, 10, 15):
+            running = int(((t[:, 0] <= end - back) & (t[:, 1] > end - back)).sum())
+            print(f"  CTAs running {back:2d} us before the end: {running}")
+print(m.counters())

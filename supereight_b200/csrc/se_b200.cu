@@ -282,7 +282,7 @@ int create_pools(se_b200_map* m) {
 }
 
 int fetch_counters(se_b200_map* m) {
-  CUDA_TRY(cudaMemcpyAsync(m->h_counters, m->p.counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaMemcpyAsync(m->h_counters, m->p.counters, kCntTake * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   return SE_B200_OK;
 }
@@ -1285,6 +1285,12 @@ int se_b200_counters(se_b200_map* m, int32_t out[8]) {
   return check_pool_error(m);
 }
 
+#ifdef SE_TIMELINE
+int se_b200_debug_timeline(se_b200_map* m, unsigned long long* out, int n) {
+  cudaStreamSynchronize(m->stream);
+  return cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * (size_t)n) == cudaSuccess ? 0 : -1;
+}
+#endif
 int se_b200_launch_count(se_b200_map* m, int64_t* out) {
   REQUIRE_MAP(m);
   if (out) *out = m->launches;

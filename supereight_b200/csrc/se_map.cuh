@@ -32,9 +32,12 @@ constexpr int kBusy = -2;
 // q = frame & 1 at  base + 32 q  -- frame f uses slot q and clears slot q ^ 1 for the next frame, so no reset launch is needed:
 //   kCntTicket  chunk tickets drawn          kCntDone  chunks finished          kCntActive  active-list length
 //   kCntMiss    length of the allocation pass's list of missing blocks (k_alloc_sdf appends, the integrate kernel creates)
+//   kCntTake    list entries handed to the integrate kernel's warps beyond each warp's first two (ActiveList::draw): kTakeClasses
+//               counters, 32 ints apart, then the same again for the other parity
 enum Counter { kCntNodes = 0, kCntBlocks = 1, kCntError = 3, kCntNewBlocksBase = 4, kCntNewNodesBase = 5,
                kCntKeys = 6, kCntKeysReport = 7, kCntLastBlocks = 10, kCntLastNodes = 11, kCntBlocksBefore = 12, kCntNodesBefore = 13,
-               kCntTicket = 32, kCntDone = 96, kCntActive = 160, kCntMiss = 224, kNumCounters = 288 };
+               kCntTicket = 32, kCntDone = 96, kCntActive = 160, kCntMiss = 224, kCntTake = 288, kNumCounters = 288 + 2 * 16 * 32 };
+constexpr int kTakeClasses = 16;      // ticket counters of ActiveList::draw, each in a 128-byte line of its own, per frame parity
 SE_HD int counter_slot(int base, int parity) { return base + 32 * parity; }
 enum ErrorBits { kErrBlockPoolFull = 1, kErrNodePoolFull = 2, kErrKeyListFull = 4, kErrMissListFull = 8 };
 
