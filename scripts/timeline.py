@@ -34,7 +34,7 @@ for f in range(frames):
             print(f"{nm:24s} min {t[:, i].min():8.1f}  median {np.median(t[:, i]):8.1f}  max {t[:, i].max():8.1f} us")
     m.raycast(poses[f], k, mu)
     if f == frames - 1:
-        n = 2400
+        n = int(os.environ.get('SE_RAY_CTAS', '2400'))
         buf = np.zeros(8 * n, np.uint64)
         assert lib.se_b200_debug_timeline(m.h, buf.ctypes.data, 8 * n) == 0
         t = buf.reshape(n, 8)[:, 5:7].astype(np.int64)
@@ -43,6 +43,9 @@ for f in range(frames):
         end = t[:, 1].max()
         print(f"raycast: {n} CTAs, kernel {end:.1f} us; CTA duration (thread 0) min {dur.min():.1f} median {np.median(dur):.1f} p90 {np.percentile(dur, 90):.1f} max {dur.max():.1f} us")
         print("  CTA starts: p50 %.1f p90 %.1f max %.1f us" % (np.median(t[:, 0]), np.percentile(t[:, 0], 90), t[:, 0].max()))
+        bands = np.array_split(np.arange(n), 8)
+        print("  mean CTA duration by eighth of the grid (top of the image first):", " ".join(f"{dur[b].mean():.1f}" for b in bands))
+        print("  longest 5 CTAs: ", [(int(i), round(float(dur[i]), 1), round(float(t[i, 0]), 1)) for i in np.argsort(dur)[-5:]], "(index, duration, start)")
         for back in (2, 4, 6, 8, 10, 15):
             running = int(((t[:, 0] <= end - back) & (t[:, 1] > end - back)).sum())
             print(f"  CTAs running {back:2d} us before the end: {running}")

@@ -130,6 +130,8 @@ struct se_b200_map {
   float rt_light[3] = {0.f, 0.f, 0.f};
   long long launches = 0;
   int grid_integrate = 0;
+  int* d_ray_sched = nullptr;             // k_raycast's launch orders [2][groups] and costs [2][groups] (RaySchedule)
+  unsigned ray_launches = 0;
   int parity = 0;
   bool stage_timing = false;            // per-stage event pairs (se_b200_set_stage_timing): off by default -- an event between two launches breaks their programmatic-dependent-launch edge
 
@@ -479,9 +481,17 @@ RaycastParams make_raycast_params(se_b200_map* m, const float* pose, const float
 template <class V, bool DENSE>
 void launch_raycast(se_b200_map* m, const RaycastParams& rp, unsigned long long* stats_dev, bool shade, V3 light) {
   const int grid = pixel_tile_blocks(m->W, m->H, kRayThreads);
-  if (stats_dev) launch_pdl(k_raycast<V, DENSE, true, false>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev, light, (uchar4*)nullptr);
-  else if (shade) launch_pdl(k_raycast<V, DENSE, false, true>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, (unsigned long long*)nullptr, light, m->rt_dev);
-  else launch_pdl(k_raycast<V, DENSE, false, false>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, (unsigned long long*)nullptr, light, (uchar4*)nullptr);
+  // the launch order of the tile groups: expensive first, from the costs of earlier launches (RaySchedule)
+  RaySchedule rs{nullptr, nullptr, nullptr, nullptr};
+  if (m->d_ray_sched && !stats_dev) {
+    const int cur = (int)(m->ray_launches & 1u), nxt = cur ^ 1;
+    rs.order = m->d_ray_sched + (size_t)cur * grid; rs.order_next = m->d_ray_sched + (size_t)nxt * grid;
+    rs.cost = m->d_ray_sched + (size_t)(2 + cur) * grid; rs.cost_prev = m->d_ray_sched + (size_t)(2 + nxt) * grid;
+    ++m->ray_launches;
+  }
+  if (stats_dev) launch_pdl(k_raycast<V, DENSE, true, false>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev, light, (uchar4*)nullptr, rs);
+  else if (shade) launch_pdl(k_raycast<V, DENSE, false, true>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, (unsigned long long*)nullptr, light, m->rt_dev, rs);
+  else launch_pdl(k_raycast<V, DENSE, false, false>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, (unsigned long long*)nullptr, light, (uchar4*)nullptr, rs);
 }
 
 template <class V>
@@ -711,6 +721,13 @@ int se_b200_create(se_b200_map** out, int field_type, int size, float dim, int W
   // (one float more than the image, always 0: "no depth sample" for the voxels the check-free SDF integrate finds outside the image -- sdf_voxel_pair)
   CREATE_TRY(cudaMalloc(&m->d_depth, (npx + 1) * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_vertex, npx * 3 * sizeof(float)));
+  if (!getenv("SE_B200_RAY_ORDER_OFF")) {
+    const int groups = pixel_tile_blocks(m->W, m->H, kRayThreads);
+    std::vector<int> init((size_t)4 * groups, 0);
+    for (int j = 0; j < 2; ++j) std::iota(init.begin() + (size_t)j * groups, init.begin() + (size_t)(j + 1) * groups, 0);
+    CREATE_TRY(cudaMalloc(&m->d_ray_sched, init.size() * sizeof(int)));
+    CREATE_TRY(cudaMemcpy(m->d_ray_sched, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   CREATE_TRY(cudaMalloc(&m->d_normal, npx * 3 * sizeof(float)));
   CREATE_TRY(cudaMalloc(&m->d_rgba, npx * sizeof(uchar4)));
   CREATE_TRY(cudaMalloc(&m->d_active_list, (size_t)m->max_blocks * sizeof(int)));
@@ -743,6 +760,7 @@ int se_b200_destroy(se_b200_map* m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->p.node_child); cudaFree(m->p.node_code); cudaFree(m->p.node_side); cudaFree(m->p.node_mask); cudaFree(m->p.node_value);
   cudaFree(m->p.block_code); cudaFree(m->p.block_coord); cudaFree(m->p.block_active); cudaFree(m->p.block_data); cudaFree(m->p.counters); cudaFree(m->p.dir); cudaFree(m->p.ndir); cudaFree(m->p.cmask);
+  cudaFree(m->d_ray_sched);
   cudaFree(m->d_depth); cudaFree(m->d_vertex); cudaFree(m->d_normal); cudaFree(m->d_rgba); cudaFree(m->d_depth_mm);
   cudaFree(m->d_active_list); cudaFree(m->d_miss); cudaFree(m->d_requests); cudaFree(m->d_logodds); cudaFree(m->d_track);
   for (int i = 0; i < 8; ++i) { cudaFree(m->d_scaled_depth[i]); cudaFree(m->d_in_vertex[i]); cudaFree(m->d_in_normal[i]); }
