@@ -23,10 +23,18 @@ for f in range(frames):
     m.preprocess(depth[f])
     m.integrate(poses[f], k, mu, f)
     if f == frames - 1:
-        n = 592
-        buf = np.zeros(8 * n, np.uint64)
-        assert lib.se_b200_debug_timeline(m.h, buf.ctypes.data, 8 * n) == 0
-        t = buf.reshape(n, 8)[:, :5].astype(np.int64)
+        n = 1200
+        buf = np.zeros(16 * n, np.uint64)
+        assert lib.se_b200_debug_timeline(m.h, buf.ctypes.data, 16 * n) == 0
+        t = buf.reshape(n, 16)[:592, :5].astype(np.int64)
+        na = 1200
+        ta = buf.reshape(-1, 16)[:na, 8:10].astype(np.int64)
+        ta = (ta - ta[:, 0].min()) / 1000.0
+        da = ta[:, 1] - ta[:, 0]
+        print(f"alloc: {na} CTAs, kernel {ta[:, 1].max():.1f} us; CTA duration min {da.min():.1f} median {np.median(da):.1f} p90 {np.percentile(da, 90):.1f} max {da.max():.1f}; starts p50 {np.median(ta[:, 0]):.1f} max {ta[:, 0].max():.1f}")
+        print("  mean CTA duration by eighth of the grid:", " ".join(f"{da[b].mean():.1f}" for b in np.array_split(np.arange(na), 8)))
+        for back in (2, 5, 10, 20):
+            print(f"  CTAs running {back:2d} us before the end: {int(((ta[:, 0] <= ta[:, 1].max() - back) & (ta[:, 1] > ta[:, 1].max() - back)).sum())}")
         t0 = t[:, 0].min()
         t = (t - t0) / 1000.0
         names = ["start", "list produced", "blocks done (warp 0)", "list complete", "nodes done"]
@@ -35,9 +43,9 @@ for f in range(frames):
     m.raycast(poses[f], k, mu)
     if f == frames - 1:
         n = int(os.environ.get('SE_RAY_CTAS', '2400'))
-        buf = np.zeros(8 * n, np.uint64)
-        assert lib.se_b200_debug_timeline(m.h, buf.ctypes.data, 8 * n) == 0
-        t = buf.reshape(n, 8)[:, 5:7].astype(np.int64)
+        buf = np.zeros(16 * n, np.uint64)
+        assert lib.se_b200_debug_timeline(m.h, buf.ctypes.data, 16 * n) == 0
+        t = buf.reshape(n, 16)[:, 5:7].astype(np.int64)
         t = (t - t[:, 0].min()) / 1000.0
         dur = t[:, 1] - t[:, 0]
         end = t[:, 1].max()

@@ -81,9 +81,9 @@ __device__ __forceinline__ void mbar_init_fence() {
 
 // ---- SE_TIMELINE builds only (scripts/timeline.py): nanosecond time stamps of kernel phases, per CTA ----
 #ifdef SE_TIMELINE
-__device__ unsigned long long g_timeline[8 * 4096];
+__device__ unsigned long long g_timeline[16 * 4096];
 __device__ __forceinline__ void timeline_mark(int slot) {
-  if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_timeline[8 * blockIdx.x + slot] = t; }
+  if (threadIdx.x == 0 && blockIdx.x < 4096) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_timeline[16 * blockIdx.x + slot] = t; }
 }
 #else
 __device__ __forceinline__ void timeline_mark(int) {}
