@@ -5,7 +5,7 @@
 # Outputs go to gpurun_out/; scripts/summarise_profiles.py <round> (run in the build container) turns them into profiles/
 # (launch lists, key-metric tables, opcode / stall summaries and profiles/traffic.json, which bench.py reads).
 set -x
-R=${1:-r2}
+R=${1:-r2b}
 mkdir -p gpurun_out
 python -c "import torch; torch.zeros(1).cuda()" > /dev/null 2>&1
 capture() {  # workload kernels-per-frame frame regex

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Last GPU call of a round, most important first: the GPU parity tier on the final library, the driver's own sequence (smoke, the
 # default bench line, the reference arm) with wall times, then the ncu evidence (scripts/make_profiles.sh).
-R=${1:-r2}
+R=${1:-r2b}
 mkdir -p gpurun_out
 python -c "import torch; torch.zeros(1).cuda()" > /dev/null 2>&1
 (time timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -6) > gpurun_out/${R}_pytest_gpu.log 2>&1

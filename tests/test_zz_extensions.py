@@ -121,3 +121,49 @@ def test_randomised_scenarios_product_against_the_reference_build(size):
                        capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " 0 with differences" in r.stdout, r.stdout[-1000:]
+
+
+@pytest.mark.parametrize("field,mu", [(SDF, 0.1), (OFUSION, 0.008)])
+def test_launch_schedule_changes_no_result(field, mu, monkeypatch):
+    """LaunchSchedule (se_kernels.cuh): the raycast -- and the OFusion allocation pass -- start their expensive tile groups first,
+    from the costs earlier launches recorded.  Only the order of execution may change: over a sequence long enough for the
+    order to be re-partitioned several times, every frame's vertex / normal maps, image and map equal those of a map created
+    with SE_B200_LAUNCH_ORDER_OFF=1 (image order, nothing recorded)."""
+    from supereight_b200 import Map, synth
+    dim, W, H = 4.8, 160, 120
+    k = scaled_k(W)
+    monkeypatch.setenv("SE_B200_LAUNCH_ORDER_OFF", "1")
+    a = Map(field, 256, dim, W, H)
+    monkeypatch.delenv("SE_B200_LAUNCH_ORDER_OFF")
+    b = Map(field, 256, dim, W, H)
+    gen = synth.box_room
+    for f in range(6):
+        d, pose = gen(f * 7, dim, W, H, k, dropout=0.01, n_frames=300)
+        for m_ in (a, b):
+            m_.preprocess(d); m_.integrate(pose, k, mu, f); m_.raycast(pose, k, mu)
+        va, na = a.vertex_normal(); vb, nb = b.vertex_normal()
+        assert va.tobytes() == vb.tobytes() and na.tobytes() == nb.tobytes(), f
+        assert np.array_equal(a.render_volume(pose, k, mu, 0.75 * mu, False), b.render_volume(pose, k, mu, 0.75 * mu, False))
+    ka, _, _, xa = a.blocks_sorted(); kb, _, _, xb = b.blocks_sorted()
+    assert np.array_equal(ka, kb)
+    if field == SDF:
+        assert xa.tobytes() == xb.tobytes()
+    assert (nb[..., 0] != -2.0).sum() > 0.2 * W * H
+
+
+def test_sdf_long_active_list_is_handed_out_dynamically():
+    """ActiveList::Cursor (se_kernels.cuh): a list longer than two entries per resident warp is handed out by ticket, with the
+    warps of an exhausted class stealing from the others.  A 1024^3 room at 320x240 gives the integrate kernel tens of thousands of
+    blocks -- several rounds on any GPU, and on the fiber executor -- and every voxel must still equal the oracle's."""
+    from supereight_b200 import synth
+    dim, mu, W, H = 4.096, 0.1, 320, 240
+    k = scaled_k(W)
+    g, o = make_pair(SDF, 1024, dim, W, H)
+    pose = None
+    for f in range(2):
+        d, pose = synth.box_room(f * 5, dim, W, H, k, dropout=0.01, n_frames=300)
+        o.preprocess(d); o.integrate(pose, k, mu, f)
+        g.preprocess(d); g.integrate(pose, k, mu, f)
+    assert g.counters()["active"] > 20000
+    from test_gpu_parity import assert_sdf_bit_exact
+    assert_sdf_bit_exact(g, o, pose, k, mu)
