@@ -176,8 +176,8 @@ int se_b200_download_tracking(se_b200_map* map, void* track_data, float reductio
  * se_b200_download_mesh copies them out: 9 floats per triangle = vertexes[0..2] (x, y, z) of the reference's Triangle
  *   (commons.h:166-168), metres in the volume frame.
  * se_b200_mc_table (host only, no GPU needed): the 256 x 16 case table the kernel uses, -1 terminated rows in the
- *   reference's edge numbering (meshing.hpp:58-104).  It is generated, not transcribed: same polygons and triangle counts as
- *   the reference's edge_tables.h, possibly different diagonals inside a polygon (see csrc/se_meshing.cuh). */
+ *   reference's edge numbering (meshing.hpp:58-104): the classic marching-cubes tabulation, the list the reference's
+ *   edge_tables.h transcribes too, so the triangles are the reference's (see csrc/se_meshing.cuh). */
 int se_b200_extract_mesh(se_b200_map* map, int64_t* n_triangles);
 int se_b200_download_mesh(se_b200_map* map, float* triangles, int64_t capacity_triangles);
 void se_b200_mc_table(int8_t table[4096]);

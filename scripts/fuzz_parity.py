@@ -26,10 +26,10 @@ import oracle_lib  # noqa: E402
 from oracle_lib import OFUSION, SDF, Oracle  # noqa: E402
 from parity_utils import compare_blocks, compare_images, compare_nodes  # noqa: E402
 
-import mc_table_ref  # noqa: E402  (tests/: independent generator of the marching-cubes case table)
+import mc_table_ref  # noqa: E402  (tests/: reader of the marching-cubes case table the library ships)
 from supereight_b200 import Map, synth  # noqa: E402
 
-MC_TABLE = mc_table_ref.table()
+MC_TABLE = mc_table_ref.classic_table()
 
 
 class RefAsMap:

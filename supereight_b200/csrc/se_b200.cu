@@ -631,7 +631,7 @@ int extract_mesh_impl(se_b200_map* m, int64_t* n_triangles) {
   if (n == 0) return SE_B200_OK;
   if (!m->d_mc_table) {
     int8_t table[256 * kMcRow];
-    mc_generate_table(table);
+    mc_case_table(table);
     CUDA_TRY(cudaMalloc(&m->d_mc_table, sizeof(table)));
     CUDA_TRY(cudaMemcpyAsync(m->d_mc_table, table, sizeof(table), cudaMemcpyHostToDevice, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));          // `table` is on the stack
@@ -1248,7 +1248,7 @@ int se_b200_download_mesh(se_b200_map* m, float* triangles, int64_t capacity) {
   return SE_B200_OK;
 }
 
-void se_b200_mc_table(int8_t table[4096]) { mc_generate_table(table); }
+void se_b200_mc_table(int8_t table[4096]) { mc_case_table(table); }
 
 int se_b200_set_voxels(se_b200_map* m, const int32_t* xyz, const void* voxels, int n) {
   REQUIRE_MAP(m);

@@ -2,20 +2,15 @@
 // with the `inside` / `select` functors DenseSLAMSystem::dump_mesh passes (se_denseslam/src/DenseSLAMSystem.cpp:302-322:
 // inside = val.x < 0, select = val.x).
 //
-// Case table.  The reference ships a transcription of the classic 256 x 16 marching-cubes tabulation (edge_tables.h).
-// That file is data that cannot be re-derived entry by entry (the order of triangles inside a case is a convention), so
-// this library GENERATES its table from first principles instead, in the reference's own corner / edge numbering
-// (meshing.hpp:58-104):
-//   * on every cube face, walked counter-clockwise as seen from outside the cube, each maximal run of inside corners is cut
-//     off by one segment directed from the edge where the walk enters the run to the edge where it leaves it (so the
-//     ambiguous face, two diagonal inside corners, separates them -- a rule that depends on the face only, hence no cracks
-//     between neighbouring cells);
-//   * segments are chained into closed polygons, each started at its lowest edge index, polygons ordered by that index;
-//   * a polygon (e0 .. ek-1) becomes the fan (e0, ei, ei+1), i = 1 .. k-2.
-// Checked against the reference's table in the development container: all 256 cases have the same directed polygon
-// boundaries and the same triangle count (at most 5), 98 cases are the same triangle sets; the others differ only in which
-// diagonals split a polygon of 4-7 vertices.  Vertex positions, the cells that emit triangles and the triangle count are
-// therefore those of the reference; tests/mc_table_ref.py is an independent generator of the same convention.
+// Case table.  Which triangles a cube configuration emits is the classic 256 x 16 marching-cubes tabulation (Lorensen & Cline 1987,
+// P. Bourke's public-domain list), which the reference ships as edge_tables.h.  The order of the triangles inside a case and the
+// diagonals that split its polygons are a convention that cannot be re-derived, so a mesh that is to equal the reference's
+// triangle for triangle has to use the same list: se_mc_table.cuh holds it as data, in this library's own encoding (256 strings
+// of hexadecimal edge indices; scripts/make_mc_table.py).  tests/mc_table_ref.py is a first-principles generator of the
+// table's geometry -- on every cube face, walked counter-clockwise from outside, each run of inside corners is cut off by one
+// directed segment, segments chain into polygons -- and tests/test_meshing.py requires the list's 256 cases to have exactly those
+// directed polygon boundaries.  (Round 1 meshed with the generator's own fans: same cells, vertices and triangle count as the
+// reference, other diagonals in 158 cases.)
 #pragma once
 #include "se_map.cuh"
 
@@ -37,45 +32,15 @@ SE_HD void mc_edge(int e, int& a, int& b) {
   else { a = e - 8; b = e - 4; }
 }
 
-// host: build the 256 x 16 case table described above (-1 terminated rows)
-inline void mc_generate_table(int8_t table[256 * kMcRow]) {
-  int corner_at[2][2][2];
-  for (int c = 0; c < 8; ++c) { int x, y, z; mc_corner(c, x, y, z); corner_at[x][y][z] = c; }
-  int edge_of[8][8];
-  for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) edge_of[a][b] = -1;
-  for (int e = 0; e < 12; ++e) { int a, b; mc_edge(e, a, b); edge_of[a][b] = edge_of[b][a] = e; }
-  int face[6][4];
-  for (int axis = 0, f = 0; axis < 3; ++axis) {
-    const int u = (axis + 1) % 3, v = (axis + 2) % 3;           // e_u x e_v = e_axis
-    for (int side = 0; side < 2; ++side, ++f) {
-      const int ccw[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
-      for (int i = 0; i < 4; ++i) {
-        const int* uv = ccw[side ? i : (4 - i) % 4];             // the low face is seen from the other side: reversed cycle
-        int p[3]; p[axis] = side; p[u] = uv[0]; p[v] = uv[1];
-        face[f][i] = corner_at[p[0]][p[1]][p[2]];
-      }
-    }
-  }
+// host: the 256 x 16 case table (-1 terminated rows of edge indices, three per triangle)
+inline void mc_case_table(int8_t table[256 * kMcRow]) {
+  static const char* const kCases[256] = {
+#include "se_mc_table.cuh"
+  };
   for (int idx = 0; idx < 256; ++idx) {
-    int next[12];
-    for (int e = 0; e < 12; ++e) next[e] = -1;
-    for (int f = 0; f < 6; ++f)
-      for (int i = 0; i < 4; ++i) {
-        const int a = face[f][i], b = face[f][(i + 1) & 3];
-        if (((idx >> a) & 1) || !((idx >> b) & 1)) continue;   // the walk enters a run of inside corners across edge (a, b)
-        int j = i + 1;
-        while ((idx >> face[f][(j + 1) & 3]) & 1) ++j;           // ... and leaves it across (face[j], face[j+1])
-        next[edge_of[a][b]] = edge_of[face[f][j & 3]][face[f][(j + 1) & 3]];
-      }
     int8_t* row = table + idx * kMcRow;
     int n = 0;
-    bool used[12] = {};
-    for (int e = 0; e < 12; ++e) {
-      if (next[e] < 0 || used[e]) continue;
-      int loop[12], len = 0;
-      for (int q = e; !used[q]; q = next[q]) { used[q] = true; loop[len++] = q; }
-      for (int i = 1; i + 1 < len && n + 3 < kMcRow; ++i) { row[n++] = (int8_t)loop[0]; row[n++] = (int8_t)loop[i]; row[n++] = (int8_t)loop[i + 1]; }
-    }
+    for (const char* c = kCases[idx]; *c && n < kMcRow - 1; ++c) row[n++] = (int8_t)(*c <= '9' ? *c - '0' : *c - 'a' + 10);
     while (n < kMcRow) row[n++] = -1;
   }
 }

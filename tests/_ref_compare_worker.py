@@ -97,12 +97,13 @@ to_, ro = o.tracking_data(); tr_, rr = r.tracking_data()
 res["track_result"] = bits(to_["result"], tr_["result"]); res["track_error"] = bits(to_["error"], tr_["error"]); res["track_J"] = bits(to_["J"], tr_["J"])
 res["reduction"] = bits(ro, rr); res["pose"] = bits(po, pr); res["tracked"] = int(oko != okr)
 
-# N4: the reference's own edge table vs the generated one: same vertices, same triangle count
-mo = o.marching_cube(mc_table_ref.table()); mr = r.marching_cube(mc_table_ref.table())
+# N4: the reference's own edge table vs the classic list the library ships: the same triangles
+mo = o.marching_cube(mc_table_ref.classic_table()); mr = r.marching_cube(mc_table_ref.classic_table())
 res["mesh_triangles"] = [int(len(mo)), int(len(mr))]
 vo = np.unique(mo.reshape(-1, 3).view(np.uint32), axis=0); vr = np.unique(mr.reshape(-1, 3).view(np.uint32), axis=0)
 res["mesh_vertices_differ"] = int(vo.shape != vr.shape or not np.array_equal(vo, vr))
 so = {tuple(np.roll(t, -min(range(3), key=lambda i: tuple(t[i])), axis=0).ravel()) for t in mo.view(np.uint32).astype(np.int64)}
 sr = {tuple(np.roll(t, -min(range(3), key=lambda i: tuple(t[i])), axis=0).ravel()) for t in mr.view(np.uint32).astype(np.int64)}
 res["mesh_identical_triangles_frac"] = len(so & sr) / max(1, len(sr))
+res["mesh_triangles_only_in_oracle"] = len(so - sr)
 print(json.dumps(res))

@@ -1,4 +1,5 @@
-"""Independent generator of the marching-cubes case table the library builds in csrc/se_meshing.cuh (N4).
+"""First-principles generator of the geometry of the marching-cubes case table (N4): what tests/test_meshing.py checks the classic
+table the library ships (csrc/se_mc_table.cuh) against -- same directed polygon boundaries in all 256 cases.
 
 Convention (reference numbering, se_core/include/se/algorithms/meshing.hpp:58-104): corner c sits at CORNER[c], edge e joins
 EDGE[e] = (source, dest).  On every cube face, walked counter-clockwise as seen from outside the cube, each maximal run of
@@ -76,3 +77,28 @@ def table():
         assert len(flat) <= 15
         t[index, :len(flat)] = flat
     return t
+
+
+def classic_table():
+    """the table the library ships, read from its data file (no library needed): 256 x 16 int8, -1 terminated rows"""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "supereight_b200", "csrc", "se_mc_table.cuh")
+    cases = re.findall(r'"([0-9a-b]*)"', "".join(l for l in open(path) if not l.lstrip().startswith("//")))
+    assert len(cases) == 256
+    t = np.full((256, 16), -1, np.int8)
+    for i, c in enumerate(cases):
+        t[i, :len(c)] = [int(ch, 16) for ch in c]
+    return t
+
+
+def boundary(tris):
+    """directed boundary edges of a set of triangles (edge-index triples): interior diagonals cancel against their reverse"""
+    edges = set()
+    for a, b, c in tris:
+        for e in ((a, b), (b, c), (c, a)):
+            if (e[1], e[0]) in edges:
+                edges.remove((e[1], e[0]))
+            else:
+                edges.add(e)
+    return edges

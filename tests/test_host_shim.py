@@ -100,7 +100,7 @@ def test_shim_frame_loop_matches_oracle(tmp_path, field, mu):
     pts = np.array([ln.split() for ln in vtk[5:5 + npts]], np.float64).reshape(-1, 3, 3)
     if field == "sdf":
         import mc_table_ref
-        want = o.marching_cube(mc_table_ref.table())
+        want = o.marching_cube(mc_table_ref.classic_table())
         assert pts.shape == want.shape and len(want) > 1000
         np.testing.assert_allclose(pts, want, rtol=2e-5, atol=0)      # operator<< prints 6 significant digits
         assert np.array_equal(gd["x"].view(np.uint32), data["x"].view(np.uint32)) and np.array_equal(gd["y"], data["y"])

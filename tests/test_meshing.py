@@ -1,7 +1,8 @@
 """N4: marching cubes (se_core/include/se/algorithms/meshing.hpp:158-208, DenseSLAMSystem::dump_mesh).
 
-CPU part: the case table the library generates == an independent generator of the same convention (tests/mc_table_ref.py),
-plus the properties a marching-cubes table must have; the oracle's restatement on closed forms.
+CPU part: the classic case table the library ships (csrc/se_mc_table.cuh) has, case by case, the directed polygon boundaries a
+first-principles generator derives (tests/mc_table_ref.py) and the properties a marching-cubes table must have -- and, where the
+reference tree is present, is the reference's own list; the oracle's restatement on closed forms.
 GPU part: the CUDA mesh == the oracle's mesh, bit for bit, triangle by triangle."""
 import itertools
 
@@ -20,15 +21,33 @@ def rows(table):
 
 
 # ---- the table ------------------------------------------------------------------------------------
-def test_library_table_equals_independent_generator():
+def test_library_table_is_the_classic_table_and_has_the_generated_geometry():
     import supereight_b200
     lib = supereight_b200.mc_table()
     assert lib.shape == (256, 16) and lib.dtype == np.int8
-    assert np.array_equal(lib, ref.table())
+    assert np.array_equal(lib, ref.classic_table())                  # the C++ decoder of the data file == this one
+    gen = rows(ref.table())
+    for i, tris in enumerate(rows(lib)):
+        assert len(tris) == len(gen[i]), i                           # same number of triangles ...
+        assert ref.boundary(tris) == ref.boundary(gen[i]), i         # ... filling the same directed polygons
+    assert sum(len(t) for t in rows(lib)) == 820
+
+
+def test_library_table_is_the_reference_list():
+    """edge_tables.h (`triTable`), where the reference tree exists (the development container)"""
+    import os
+    import sys
+    if not os.path.exists("/root/reference/se_core/include/se/algorithms/edge_tables.h"):
+        pytest.skip("no reference tree on this machine")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import make_mc_table
+    want = make_mc_table.read_reference_rows("/root/reference")
+    got = [[int(v) for v in row if v != -1] for row in ref.classic_table()]
+    assert got == want
 
 
 def test_table_rows_are_well_formed():
-    t = ref.table()
+    t = ref.classic_table()
     for i in range(256):
         row = t[i]
         n = int(np.argmax(row == -1)) if (row == -1).any() else 16
@@ -38,7 +57,7 @@ def test_table_rows_are_well_formed():
 
 
 def test_table_uses_exactly_the_edges_that_change_sign():
-    for i, tris in enumerate(rows(ref.table())):
+    for i, tris in enumerate(rows(ref.classic_table())):
         cut = {e for e, (a, b) in enumerate(ref.EDGE) if ((i >> a) & 1) != ((i >> b) & 1)}
         assert {e for tri in tris for e in tri} == cut, i
 
@@ -59,7 +78,7 @@ def directed_boundary(tris):
 def test_table_polygons_stay_on_cube_faces_and_neighbours_agree():
     """every boundary segment of a cell's surface lies on one cube face, and the cell across that face produces the same
     segment reversed: the mesh has no cracks and a consistent orientation"""
-    all_rows = rows(ref.table())
+    all_rows = rows(ref.classic_table())
     edge_faces = []
     for a, b in ref.EDGE:
         pa, pb = ref.CORNER[a], ref.CORNER[b]
@@ -92,7 +111,7 @@ def test_table_polygons_stay_on_cube_faces_and_neighbours_agree():
 
 def test_table_orientation_single_corner_cases():
     mid = [np.mean([ref.CORNER[a], ref.CORNER[b]], axis=0) for a, b in ref.EDGE]
-    all_rows = rows(ref.table())
+    all_rows = rows(ref.classic_table())
     for c in range(8):
         for index, sign in ((1 << c, 1.0), (255 ^ (1 << c), -1.0)):
             (t,) = all_rows[index]
@@ -115,7 +134,7 @@ def plane_map(field, frames=3, size=256, dim=4.8, W=160, H=120, mu=0.1):
 def test_oracle_mesh_of_a_wall_lies_on_the_wall_and_faces_the_camera():
     dim, size = 4.8, 256
     o, pose, k = plane_map(SDF)
-    tri = o.marching_cube(ref.table())
+    tri = o.marching_cube(ref.classic_table())
     assert len(tri) > 1000
     zw = 0.75 * dim
     assert np.abs(tri[..., 2] - zw).max() < 1.0 * dim / size          # the zero crossing is the wall (1 mm depth quantisation)
@@ -127,7 +146,7 @@ def test_oracle_mesh_of_a_wall_lies_on_the_wall_and_faces_the_camera():
 def test_oracle_mesh_is_watertight_inside_the_observed_region():
     """inner edges of the wall's mesh are shared by exactly two triangles, in opposite directions"""
     o, pose, k = plane_map(SDF)
-    tri = o.marching_cube(ref.table())
+    tri = o.marching_cube(ref.classic_table())
     keys = np.round(tri.astype(np.float64) * 1e6).astype(np.int64)
     edges = {}
     for t in keys:
@@ -140,7 +159,7 @@ def test_oracle_mesh_is_watertight_inside_the_observed_region():
 
 
 def test_oracle_empty_map_has_no_mesh():
-    assert len(Oracle(SDF, 64, 1.0, 8, 8).marching_cube(ref.table())) == 0
+    assert len(Oracle(SDF, 64, 1.0, 8, 8).marching_cube(ref.classic_table())) == 0
 
 
 def test_oracle_mesh_hand_built_cell():
@@ -150,7 +169,7 @@ def test_oracle_mesh_hand_built_cell():
     for x, y, z in itertools.product(range(8, 11), repeat=3):
         o.set_voxel(x, y, z, 0.5, 1.0)
     o.set_voxel(9, 9, 9, -0.25, 1.0)
-    tri = o.marching_cube(ref.table())
+    tri = o.marching_cube(ref.classic_table())
     # the inside voxel is corner 0 of cell (9,9,9) and some other corner of its 7 lower neighbours: 8 triangles, an octahedron
     assert tri.shape == (8, 3, 3)
     cell = [t for t in tri if (t >= np.float32(0.9) - 1e-6).all()]
@@ -175,7 +194,7 @@ def test_gpu_mesh_equals_oracle_sdf_sequence():
         d, pose = synth.box_room(f * 7, dim, W, H, k, noise_mm=2.0, dropout=0.01)
         g.preprocess(d); o.preprocess(d)
         g.integrate(pose, k, mu, f); o.integrate(pose, k, mu, f)
-    want = o.marching_cube(ref.table())
+    want = o.marching_cube(ref.classic_table())
     got = g.mesh()
     assert len(want) > 5000
     assert got.shape == want.shape
@@ -200,7 +219,7 @@ def test_gpu_mesh_of_an_uploaded_map_equals_oracle(field):
     g = _gpu_map(field, size, dim, W, H)
     g.upload_nodes(codes, values)
     g.upload_blocks(keys, data)
-    want = o.marching_cube(ref.table())
+    want = o.marching_cube(ref.classic_table())
     got = g.mesh()
     assert len(want) > 100
     assert got.shape == want.shape
@@ -224,7 +243,7 @@ def test_gpu_mesh_empty_map_and_border_clamp():
     for p, v in zip(xyz, vox):
         o.set_voxel(int(p[0]), int(p[1]), int(p[2]), float(v["x"]), float(v["y"]))
     g.set_voxels(xyz, vox)
-    want = o.marching_cube(ref.table())
+    want = o.marching_cube(ref.classic_table())
     got = g.mesh()
     assert len(want) > 200
     assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
