@@ -123,6 +123,8 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("SE_B200_BENCH_NO_SAMPLER"):      # (diagnostic: how much the 10 ms NVML polling disturbs the host-timed legs)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -464,11 +466,15 @@ def run_gpu(args, cfg, rank, world, local_rank):
     res = legs.resident(render_target=True)
     res_plain = legs.resident(render_target=False)
     stage_ms, stage_bytes, units = legs.stages()
-    # e2e: the four stock calls.  (Round 2: the loop with the render target -- the raycast kernel writing the image to host memory as
-    # the rays finish -- is measured beside it.  It does not win any more: the 1.2 MB image needs ~22 us of PCIe time, which a
-    # 31 us raycast that starts its expensive rays first no longer hides; scripts/e2e_steps.py, profiles/r2b_e2e_ab.log.)
-    e2e = legs.host_loop("pinned", render_target=False)
-    e2e_rt = legs.host_loop("pinned", render_target=True)
+    # e2e: the four stock calls on the caller's own (malloc'd) buffers, page-locked once with se_b200_register_host_buffer -- what
+    # se_b200_benchmark.cpp does with the buffers se_apps/src/benchmark.cpp:90-97 allocates.  (Round 2: the loop with the render
+    # target -- the raycast kernel writing the image to host memory as the rays finish -- is measured beside it.  It does not win
+    # any more: the 1.2 MB image needs ~22 us of PCIe time, which a 31 us raycast that starts its expensive rays first no longer
+    # hides.  And buffers from torch's pinned allocator, the first headline, are measured beside it too: over a run's first frames
+    # they are slower and jittery on these boxes -- 0.19 against 0.142 ms per frame over frames 5..24, the same over 300 frames;
+    # scripts/e2e_order.py, profiles/r2b_e2e_order.log.)
+    e2e = legs.host_loop("registered", render_target=False)
+    e2e_rt = legs.host_loop("registered", render_target=True)
     clocks = sampler.stop()                 # sampled over the timed regions above (resident and end-to-end)
     notes = {}
 
@@ -480,7 +486,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
             return None
 
     e2e_pageable = optional("e2e_pageable", lambda: legs.host_loop("pageable", render_target=False))
-    e2e_registered = optional("e2e_registered", lambda: legs.host_loop("registered", render_target=False))
+    e2e_torch_pinned = optional("e2e_torch_pinned", lambda: legs.host_loop("pinned", render_target=False))
     ov = optional("e2e_overlapped", legs.host_overlapped)
     barrier()
 
@@ -523,14 +529,15 @@ def run_gpu(args, cfg, rank, world, local_rank):
             "value_without_render_target": {"value": round(aggregate_value(world, steps, plain_ms_max), 2), "ms_per_step": round(plain_ms_max / steps, 5),
                                             "gpu_launches": int(res_plain["launches"]), "note": "the same loop with the separate shading kernel"},
             "e2e": e2e_entry(e2e, "synchronous se_b200_preprocess_depth_host, se_b200_integrate, se_b200_raycast, se_b200_render_volume_host per frame (the "
-                                  "reference's stage semantics), pinned buffers: depth copied in by preprocess, the image written to the caller's "
-                                  "buffer by renderVolume's shading kernel", e2e_ms_max, {"h2d_bytes_per_step": W * H * 2, "d2h_bytes_per_step": W * H * 4}),
+                                  "reference's stage semantics) on host buffers page-locked once with se_b200_register_host_buffer (pinned host "
+                                  "memory): depth copied in by preprocess, the image written to the caller's buffer by renderVolume's shading "
+                                  "kernel", e2e_ms_max, {"h2d_bytes_per_step": W * H * 2, "d2h_bytes_per_step": W * H * 4}),
             "e2e_render_target": e2e_entry(e2e_rt, "the same loop with se_b200_set_render_target(the output buffer) set once: the raycast kernel writes "
                                                    "the image to host memory as the rays finish, renderVolume waits for it", e2e_rt_ms_max),
             "e2e_pageable": e2e_entry(e2e_pageable, "the same loop with malloc'd buffers, as se_apps/src/benchmark.cpp:90-97 allocates them (staged copies)")
                             or {"unavailable": notes.get("e2e_pageable")},
-            "e2e_registered": e2e_entry(e2e_registered, "malloc'd buffers page-locked once with se_b200_register_host_buffer")
-                              or {"unavailable": notes.get("e2e_registered")},
+            "e2e_torch_pinned": e2e_entry(e2e_torch_pinned, "the same loop on buffers from torch's pinned allocator (tensor.pin_memory())")
+                                or {"unavailable": notes.get("e2e_torch_pinned")},
             "e2e_overlapped": ({"value": round(aggregate_value(world, steps, ov_ms_max), 2), "unit": UNIT, "ms_per_step": round(ov_ms_max / steps, 5),
                                 "result_checksum": ov["checksum"],
                                 "api": "se_b200_preprocess_depth_host_async + se_b200_render_volume_host_async (copy streams, double-buffered); "
@@ -565,7 +572,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
                 xl = GpuLegs(name, xcfg, 0, local_rank, args.extra_steps, 5, stream, flush, barrier)
                 r = xl.resident(render_target=True)
                 sms, sby, xunits = xl.stages()
-                xe = xl.host_loop("pinned", render_target=False)
+                xe = xl.host_loop("registered", render_target=False)
                 k = kernel_table(name, sms, sby, peak)
                 xconf = config_of(name, xcfg, 1)
                 ms = sum(r["step_ms"]) / len(r["step_ms"])

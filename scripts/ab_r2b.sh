@@ -21,7 +21,7 @@ for spec in "$@"; do
     for lib in in-tree $(ls supereight_b200/variants/*.so 2>/dev/null); do
       echo "== $WL steps $STEPS lib $lib rep $rep" >> $LOG
       if [ "$lib" = in-tree ]; then unset SE_B200_LIB; else export SE_B200_LIB=$PWD/$lib; fi
-      timeout 600 python bench.py --workload $WL --steps $STEPS --warmup 5 --no-extra --no-cpu-baseline 2>&1 | summ >> $LOG 2>&1
+      timeout 600 python bench.py --workload $WL --steps $STEPS --warmup ${WARMUP:-5} --no-extra --no-cpu-baseline 2>&1 | summ >> $LOG 2>&1
     done
   done
 done

@@ -401,9 +401,7 @@ int integrate_impl(se_b200_map* m, const float* pose_p, const float* k, float mu
   if (m->pending_mm && m->pending_upload) CUDA_TRY(cudaStreamWaitEvent(as, m->pending_upload, 0));
   m->depth_read_valid = false; m->depth_ready_valid = false;
   if (FieldTraits<V>::is_sdf) {
-    // (image order: every ray of this pass marches the same number of samples, and the look-up of its tile group at the start of
-    // each 4 us CTA costs more than the tail it removes -- measured, round 2: 21.1 -> 24.1 us at 512^3 with the schedule, 64.6 -> 55.4 us at 2048^3)
-    launch_pdl(k_alloc_sdf<V>, grid_px, threads, 0, as, view, m->d_depth, src, ap, miss, parity, LaunchSchedule{nullptr, nullptr, nullptr, nullptr});
+    launch_pdl(k_alloc_sdf<V>, grid_px, threads, 0, as, view, m->d_depth, src, ap, miss, parity);
     if (int r = check_launch(m)) return r;
   } else {
     // (expensive tile groups first: these rays are of very different lengths -- 87 -> 63 us at 1024^3)
