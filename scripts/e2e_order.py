@@ -1,3 +1,7 @@
+"""bench.py's synchronous end-to-end leg (20 steps after 5 warm-up frames, as the driver runs it) for a sequence of buffer kinds in ONE
+process: which host buffers the loop is fast and steady on, and whether the order of the legs matters.
+Usage: python scripts/e2e_order.py pinned,registered,pinned,resident,sleep,...   (pinned = torch's pinned allocator, registered =
+numpy + se_b200_register_host_buffer, pageable; resident / stages = the device-timed legs; sleep = half a second of nothing)"""
 import os, sys, time
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch
