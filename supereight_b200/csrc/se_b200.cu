@@ -503,7 +503,7 @@ RaycastParams make_raycast_params(se_b200_map* m, const float* pose, const float
 template <class V, bool DENSE>
 void launch_raycast(se_b200_map* m, const RaycastParams& rp, unsigned long long* stats_dev, bool shade, V3 light) {
   const int grid = pixel_tile_blocks(m->W, m->H, kRayThreads);
-  // the launch order of the tile groups: expensive first, from the costs of earlier launches (RaySchedule)
+  // the launch order of the tile groups: expensive first, from the costs of earlier launches (LaunchSchedule)
   const LaunchSchedule rs = stats_dev ? LaunchSchedule{nullptr, nullptr, nullptr, nullptr} : next_schedule(m->d_ray_sched, grid, m->ray_launches);
   if (stats_dev) launch_pdl(k_raycast<V, DENSE, true, false>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, stats_dev, light, (uchar4*)nullptr, rs);
   else if (shade) launch_pdl(k_raycast<V, DENSE, false, true>, grid, kRayThreads, 0, m->stream, m->view<V>(), rp, m->d_vertex, m->d_normal, (unsigned long long*)nullptr, light, m->rt_dev, rs);
